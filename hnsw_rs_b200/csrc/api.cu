@@ -1,0 +1,1057 @@
+// C ABI of libhnsw_b200.so (see include/hnsw_b200.h).  Host-side glue only: argument
+// checks, device memory, format I/O.  All arithmetic of the hot path runs in the
+// kernels of kernels.cu / builder.cu; there is deliberately no CPU fallback.
+#include <dirent.h>
+#include <errno.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/stat.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "engine.h"
+
+namespace hb {
+static thread_local std::string g_err;
+void set_error(const std::string& s) { g_err = s; }
+int cuda_fail(cudaError_t e, const char* what) {
+    g_err = std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what;
+    return HNSWB200_ECUDA;
+}
+static int fail(int code, const std::string& s) {
+    g_err = s;
+    return code;
+}
+}  // namespace hb
+using namespace hb;
+
+int hnswb200_ctx::ws_reserve(size_t bytes) {
+    if (bytes <= ws_bytes) return 0;
+    if (d_ws) { cudaStreamSynchronize(stream); cudaFree(d_ws); d_ws = nullptr; ws_bytes = 0; }
+    size_t want = bytes + bytes / 4;
+    cudaError_t e = cudaMalloc(&d_ws, want);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(workspace)");
+    ws_bytes = want;
+    return 0;
+}
+
+int hnswb200_ctx::use() const {
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    return 0;
+}
+
+extern "C" {
+
+const char* hnswb200_last_error(void) { return g_err.c_str(); }
+int hnswb200_version(void) { return 100; }
+
+// ---------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------
+int hnswb200_ctx_create(int device, hnswb200_ctx** out) {
+    if (!out) return fail(HNSWB200_EINVAL, "ctx_create: out is NULL");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(HNSWB200_ECUDA, std::string("no CUDA device available (this library has no CPU fallback): ") +
+                                        cudaGetErrorString(e));
+    if (device < 0 || device >= count) return fail(HNSWB200_EINVAL, "ctx_create: bad device index");
+    hnswb200_ctx* c = new hnswb200_ctx();
+    c->device = device;
+    HB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    HB_CUDA(cudaGetDeviceProperties(&prop, device));
+    c->num_sms = prop.multiProcessorCount;
+    HB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->own_stream = true;
+    HB_CUDA(cudaMalloc((void**)&c->d_scratch, 64 * sizeof(uint32_t)));
+    HB_CUDA(cudaMemset(c->d_scratch, 0, 64 * sizeof(uint32_t)));
+    *out = c;
+    return 0;
+}
+
+void hnswb200_ctx_destroy(hnswb200_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    if (c->d_scratch) cudaFree(c->d_scratch);
+    if (c->d_ws) cudaFree(c->d_ws);
+    delete c;
+}
+
+int hnswb200_ctx_set_stream(hnswb200_ctx* c, void* s) {
+    if (!c) return fail(HNSWB200_EINVAL, "ctx is NULL");
+    if (c->own_stream && c->stream) {
+        cudaStreamSynchronize(c->stream);
+        cudaStreamDestroy(c->stream);
+    }
+    c->stream = (cudaStream_t)s;
+    c->own_stream = false;
+    return 0;
+}
+
+int hnswb200_ctx_sync(hnswb200_ctx* c) {
+    if (!c) return fail(HNSWB200_EINVAL, "ctx is NULL");
+    if (c->use()) return HNSWB200_ECUDA;
+    HB_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+int hnswb200_ctx_device(const hnswb200_ctx* c) { return c ? c->device : -1; }
+
+void hnswb200_params_default(uint64_t m, int64_t ef_cons, uint64_t dim, hnswb200_params* p) {
+    p->ep = 0;
+    p->m = m;
+    p->mmax = m;
+    p->mmax0 = 2 * m;
+    p->ml = 1.0f / logf((float)m);  // params.rs:15-17
+    p->ef_cons = ef_cons >= 0 ? (uint64_t)ef_cons : 2 * m;
+    p->dim = dim;
+}
+
+// ---------------------------------------------------------------------------
+// vectors
+// ---------------------------------------------------------------------------
+int hnswb200_quantise(hnswb200_ctx* c, const float* rows, uint64_t n, uint32_t dim, uint8_t* codes,
+                      float* mins, float* deltas) {
+    if (!c || !rows || !codes || !mins || !deltas) return fail(HNSWB200_EINVAL, "quantise: NULL argument");
+    if (dim == 0) return fail(HNSWB200_EINVAL, "quantise: cannot quantise an empty vector");
+    if (n == 0) return 0;
+    if (c->use()) return HNSWB200_ECUDA;
+    RecLayout L = hb_make_layout(dim);
+    DevBuf<float> d_rows, d_mins, d_deltas;
+    DevBuf<uint8_t> d_codes;
+    HB_CUDA(d_rows.alloc(n * dim));
+    HB_CUDA(d_codes.alloc(n * dim));
+    HB_CUDA(d_mins.alloc(n));
+    HB_CUDA(d_deltas.alloc(n));
+    uint32_t* nan_flag = c->d_scratch + 1;
+    HB_CUDA(cudaMemsetAsync(nan_flag, 0, 4, c->stream));
+    HB_CUDA(cudaMemcpyAsync(d_rows.p, rows, n * dim * 4, cudaMemcpyHostToDevice, c->stream));
+    HB_CUDA(launch_quantise(d_rows.p, n, L, nullptr, d_codes.p, d_mins.p, d_deltas.p, nan_flag, c->stream));
+    HB_CUDA(cudaMemcpyAsync(codes, d_codes.p, n * dim, cudaMemcpyDeviceToHost, c->stream));
+    HB_CUDA(cudaMemcpyAsync(mins, d_mins.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    HB_CUDA(cudaMemcpyAsync(deltas, d_deltas.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    uint32_t flag = 0;
+    HB_CUDA(cudaMemcpyAsync(&flag, nan_flag, 4, cudaMemcpyDeviceToHost, c->stream));
+    HB_CUDA(cudaStreamSynchronize(c->stream));
+    if (flag) return fail(HNSWB200_EINVAL, "quantise: NaN in vector (the reference panics in partial_cmp().unwrap())");
+    return 0;
+}
+
+int hnswb200_dist_full_pairs(hnswb200_ctx* c, const float* x, const float* y, uint64_t n, uint32_t dim,
+                             float* out) {
+    if (!c || !x || !y || !out) return fail(HNSWB200_EINVAL, "dist_full_pairs: NULL argument");
+    if (n == 0) return 0;
+    if (c->use()) return HNSWB200_ECUDA;
+    DevBuf<float> dx, dy, dout;
+    HB_CUDA(dx.alloc(n * dim));
+    HB_CUDA(dy.alloc(n * dim));
+    HB_CUDA(dout.alloc(n));
+    HB_CUDA(cudaMemcpyAsync(dx.p, x, n * dim * 4, cudaMemcpyHostToDevice, c->stream));
+    HB_CUDA(cudaMemcpyAsync(dy.p, y, n * dim * 4, cudaMemcpyHostToDevice, c->stream));
+    HB_CUDA(launch_dist_full_pairs(dx.p, dy.p, n, dim, dout.p, c->stream));
+    HB_CUDA(cudaMemcpyAsync(out, dout.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    HB_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// points
+// ---------------------------------------------------------------------------
+}  // extern "C"
+
+int hnswb200_points::reserve(uint64_t want) {
+    if (want <= cap) return 0;
+    uint64_t ncap = std::max<uint64_t>(want, cap + cap / 2);
+    uint8_t* nrec = nullptr;
+    HB_CUDA(cudaMalloc((void**)&nrec, std::max<uint64_t>(ncap, 1) * L.stride));
+    HB_CUDA(cudaMemsetAsync(nrec, 0, ncap * L.stride, ctx->stream));
+    if (d_rec && n) HB_CUDA(cudaMemcpyAsync(nrec, d_rec, n * L.stride, cudaMemcpyDeviceToDevice, ctx->stream));
+    HB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (d_rec) cudaFree(d_rec);
+    d_rec = nrec;
+    cap = ncap;
+    return 0;
+}
+
+static int points_new(hnswb200_ctx* c, uint32_t dim, uint64_t n, hnswb200_points** out) {
+    if (dim == 0) return fail(HNSWB200_EINVAL, "points: dimension 0");
+    if (n >= (1ull << 31)) return fail(HNSWB200_EINVAL, "points: more than 2^31-1 points");
+    hnswb200_points* p = new hnswb200_points();
+    p->ctx = c;
+    p->L = hb_make_layout(dim);
+    int rc = p->reserve(n);
+    if (rc) { delete p; return rc; }
+    *out = p;
+    return 0;
+}
+
+// append n rows, quantised on the device
+int hb::points_append_f32(hnswb200_ctx* c, hnswb200_points* p, const float* rows, uint64_t n,
+                          const uint8_t* levels) {
+    if (n == 0) return 0;
+    if (p->n + n >= (1ull << 31)) return fail(HNSWB200_EINVAL, "points: more than 2^31-1 points");
+    int rc = p->reserve(p->n + n);
+    if (rc) return rc;
+    uint32_t* nan_flag = c->d_scratch + 1;
+    HB_CUDA(cudaMemsetAsync(nan_flag, 0, 4, c->stream));
+    const uint64_t CH = 1u << 20;  // stage through a bounded device buffer
+    DevBuf<float> d_rows;
+    HB_CUDA(d_rows.alloc(std::min(n, CH) * p->L.dim));
+    for (uint64_t s = 0; s < n; s += CH) {
+        uint64_t cnt = std::min(CH, n - s);
+        HB_CUDA(cudaMemcpyAsync(d_rows.p, rows + s * p->L.dim, cnt * p->L.dim * 4, cudaMemcpyHostToDevice, c->stream));
+        HB_CUDA(launch_quantise(d_rows.p, cnt, p->L, p->d_rec + (p->n + s) * p->L.stride, nullptr, nullptr,
+                                nullptr, nan_flag, c->stream));
+    }
+    uint32_t flag = 0;
+    HB_CUDA(cudaMemcpyAsync(&flag, nan_flag, 4, cudaMemcpyDeviceToHost, c->stream));
+    HB_CUDA(cudaStreamSynchronize(c->stream));
+    if (flag) return fail(HNSWB200_EINVAL, "NaN in vector (the reference panics in partial_cmp().unwrap())");
+    for (uint64_t i = 0; i < n; ++i) p->levels.push_back(levels ? levels[i] : 0);
+    p->n += n;
+    return 0;
+}
+
+extern "C" {
+
+int hnswb200_points_upload(hnswb200_ctx* c, const uint8_t* codes, const float* mins, const float* deltas,
+                           const uint8_t* levels, uint64_t n, uint32_t dim, hnswb200_points** out) {
+    if (!c || !out || (n && (!codes || !mins || !deltas))) return fail(HNSWB200_EINVAL, "points_upload: NULL argument");
+    if (c->use()) return HNSWB200_ECUDA;
+    hnswb200_points* p = nullptr;
+    int rc = points_new(c, dim, n, &p);
+    if (rc) return rc;
+    if (n) {
+        DevBuf<uint8_t> d_codes;
+        DevBuf<float> d_mins, d_deltas;
+        cudaError_t e;
+        if ((e = d_codes.alloc(n * dim)) != cudaSuccess || (e = d_mins.alloc(n)) != cudaSuccess ||
+            (e = d_deltas.alloc(n)) != cudaSuccess) { hnswb200_points_destroy(p); return cuda_fail(e, "cudaMalloc"); }
+        cudaMemcpyAsync(d_codes.p, codes, n * dim, cudaMemcpyHostToDevice, c->stream);
+        cudaMemcpyAsync(d_mins.p, mins, n * 4, cudaMemcpyHostToDevice, c->stream);
+        cudaMemcpyAsync(d_deltas.p, deltas, n * 4, cudaMemcpyHostToDevice, c->stream);
+        launch_pack(d_codes.p, d_mins.p, d_deltas.p, n, p->L, p->d_rec, c->stream);
+        e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) { hnswb200_points_destroy(p); return cuda_fail(e, "points_upload"); }
+    }
+    p->levels.assign(n, 0);
+    if (levels) memcpy(p->levels.data(), levels, n);
+    p->n = n;
+    *out = p;
+    return 0;
+}
+
+int hnswb200_points_from_f32(hnswb200_ctx* c, const float* rows, uint64_t n, uint32_t dim,
+                             const uint8_t* levels, hnswb200_points** out) {
+    if (!c || !out || (n && !rows)) return fail(HNSWB200_EINVAL, "points_from_f32: NULL argument");
+    if (c->use()) return HNSWB200_ECUDA;
+    hnswb200_points* p = nullptr;
+    int rc = points_new(c, dim, n, &p);
+    if (rc) return rc;
+    rc = points_append_f32(c, p, rows, n, levels);
+    if (rc) { hnswb200_points_destroy(p); return rc; }
+    *out = p;
+    return 0;
+}
+
+int hnswb200_points_download(hnswb200_ctx* c, const hnswb200_points* p, uint8_t* codes, float* mins,
+                             float* deltas, uint8_t* levels) {
+    if (!c || !p) return fail(HNSWB200_EINVAL, "points_download: NULL argument");
+    if (c->use()) return HNSWB200_ECUDA;
+    uint64_t n = p->n;
+    if (levels && n) memcpy(levels, p->levels.data(), n);
+    if (n == 0 || (!codes && !mins && !deltas)) return 0;
+    DevBuf<uint8_t> d_codes;
+    DevBuf<float> d_mins, d_deltas;
+    HB_CUDA(d_codes.alloc(n * p->L.dim));
+    HB_CUDA(d_mins.alloc(n));
+    HB_CUDA(d_deltas.alloc(n));
+    HB_CUDA(launch_unpack(p->d_rec, n, p->L, d_codes.p, d_mins.p, d_deltas.p, c->stream));
+    if (codes) HB_CUDA(cudaMemcpyAsync(codes, d_codes.p, n * p->L.dim, cudaMemcpyDeviceToHost, c->stream));
+    if (mins) HB_CUDA(cudaMemcpyAsync(mins, d_mins.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (deltas) HB_CUDA(cudaMemcpyAsync(deltas, d_deltas.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    HB_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+uint64_t hnswb200_points_len(const hnswb200_points* p) { return p ? p->n : 0; }
+uint32_t hnswb200_points_dim(const hnswb200_points* p) { return p ? p->L.dim : 0; }
+void hnswb200_points_destroy(hnswb200_points* p) {
+    if (!p) return;
+    if (p->ctx) cudaSetDevice(p->ctx->device);
+    if (p->d_rec) cudaFree(p->d_rec);
+    delete p;
+}
+
+int hnswb200_dist_pairs(hnswb200_ctx* c, const hnswb200_points* p, const uint32_t* a, const uint32_t* b,
+                        uint64_t n, float* out) {
+    if (!c || !p || (n && (!a || !b || !out))) return fail(HNSWB200_EINVAL, "dist_pairs: NULL argument");
+    if (n == 0) return 0;
+    for (uint64_t i = 0; i < n; ++i)
+        if (a[i] >= p->n || b[i] >= p->n) return fail(HNSWB200_EINVAL, "dist_pairs: point id out of range (Points::distance returns None)");
+    if (c->use()) return HNSWB200_ECUDA;
+    DevBuf<uint32_t> da, db;
+    DevBuf<float> dout;
+    HB_CUDA(da.alloc(n));
+    HB_CUDA(db.alloc(n));
+    HB_CUDA(dout.alloc(n));
+    HB_CUDA(cudaMemcpyAsync(da.p, a, n * 4, cudaMemcpyHostToDevice, c->stream));
+    HB_CUDA(cudaMemcpyAsync(db.p, b, n * 4, cudaMemcpyHostToDevice, c->stream));
+    HB_CUDA(launch_dist_pairs(p->d_rec, p->L, da.p, db.p, n, dout.p, c->stream));
+    HB_CUDA(cudaMemcpyAsync(out, dout.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    HB_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int hnswb200_dist_query_many(hnswb200_ctx* c, const hnswb200_points* p, const float* query,
+                             const uint32_t* ids, uint64_t n, float* out) {
+    if (!c || !p || !query || (n && (!ids || !out))) return fail(HNSWB200_EINVAL, "dist_query_many: NULL argument");
+    if (n == 0) return 0;
+    for (uint64_t i = 0; i < n; ++i)
+        if (ids[i] >= p->n) return fail(HNSWB200_EINVAL, "dist_query_many: point id out of range (distance2point returns None)");
+    if (c->use()) return HNSWB200_ECUDA;
+    DevBuf<uint32_t> dids;
+    DevBuf<float> dq, dout;
+    HB_CUDA(dids.alloc(n));
+    HB_CUDA(dq.alloc(p->L.dim));
+    HB_CUDA(dout.alloc(n));
+    uint32_t* nan_flag = c->d_scratch + 1;
+    HB_CUDA(cudaMemsetAsync(nan_flag, 0, 4, c->stream));
+    HB_CUDA(cudaMemcpyAsync(dids.p, ids, n * 4, cudaMemcpyHostToDevice, c->stream));
+    HB_CUDA(cudaMemcpyAsync(dq.p, query, p->L.dim * 4, cudaMemcpyHostToDevice, c->stream));
+    HB_CUDA(launch_dist_query_many(p->d_rec, p->L, dq.p, dids.p, n, dout.p, nan_flag, c->stream));
+    HB_CUDA(cudaMemcpyAsync(out, dout.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    uint32_t flag = 0;
+    HB_CUDA(cudaMemcpyAsync(&flag, nan_flag, 4, cudaMemcpyDeviceToHost, c->stream));
+    HB_CUDA(cudaStreamSynchronize(c->stream));
+    if (flag) return fail(HNSWB200_EINVAL, "dist_query_many: NaN in query");
+    return 0;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------
+// graph: device mirror of hb::HostGraph
+// ---------------------------------------------------------------------------
+hb::DevGraph hnswb200_graph::view() const {
+    hb::DevGraph g;
+    g.adj0 = d_adj0;
+    g.S0 = h.a0.S;
+    g.upper_off = d_upper_off;
+    g.upper_adj = d_adju;
+    g.SU = h.au.S;
+    g.n_layers = h.n_layers();
+    return g;
+}
+
+void hnswb200_graph::free_device() {
+    if (ctx) cudaSetDevice(ctx->device);
+    if (d_adj0) cudaFree(d_adj0);
+    if (d_upper_off) cudaFree(d_upper_off);
+    if (d_adju) cudaFree(d_adju);
+    d_adj0 = d_upper_off = d_adju = nullptr;
+    device_valid = false;
+}
+
+namespace {
+// Write row `row` of store `s` in device form into dst (S slots) and, when the degree
+// exceeds S, into continuation rows (the last slot of a full row is CHAIN | next_row).
+// `alloc_chain` hands out continuation row indices.  Returns false if none are left.
+struct RowSink {
+    virtual void put(uint64_t dev_row, const uint32_t* slots) = 0;
+};
+bool materialise_row(const hb::AdjStore& s, uint32_t row, uint64_t chain_base, uint64_t chain_cap,
+                     uint64_t& chain_used, std::unordered_map<uint32_t, std::vector<uint32_t>>& chains,
+                     RowSink& sink) {
+    const uint32_t S = s.S, d = s.deg[row];
+    std::vector<uint32_t> slots(S, hb::H_EMPTY);
+    if (d <= S) {
+        for (uint32_t i = 0; i < d; ++i) slots[i] = s.get(row, i);
+        sink.put(row, slots.data());
+        return true;
+    }
+    std::vector<uint32_t>& ch = chains[row];
+    uint32_t i = 0;
+    uint64_t cur = row;
+    size_t ci = 0;
+    while (true) {
+        uint32_t left = d - i;
+        std::fill(slots.begin(), slots.end(), hb::H_EMPTY);
+        if (left <= S) {
+            for (uint32_t j = 0; j < left; ++j) slots[j] = s.get(row, i + j);
+            sink.put(cur, slots.data());
+            return true;
+        }
+        for (uint32_t j = 0; j < S - 1; ++j) slots[j] = s.get(row, i + j);
+        i += S - 1;
+        if (ci >= ch.size()) {
+            if (chain_used >= chain_cap) return false;
+            ch.push_back((uint32_t)(chain_base + chain_used++));
+        }
+        uint32_t nxt = ch[ci++];
+        slots[S - 1] = 0x80000000u | nxt;
+        sink.put(cur, slots.data());
+        cur = nxt;
+    }
+}
+struct VecSink : RowSink {
+    std::vector<uint32_t>& v;
+    uint32_t S;
+    VecSink(std::vector<uint32_t>& v_, uint32_t S_) : v(v_), S(S_) {}
+    void put(uint64_t r, const uint32_t* slots) override { memcpy(&v[r * S], slots, S * 4); }
+};
+struct ListSink : RowSink {
+    std::vector<uint32_t>& rows;
+    std::vector<uint32_t>& data;
+    uint32_t S;
+    ListSink(std::vector<uint32_t>& r, std::vector<uint32_t>& d, uint32_t S_) : rows(r), data(d), S(S_) {}
+    void put(uint64_t r, const uint32_t* slots) override {
+        rows.push_back((uint32_t)r);
+        data.insert(data.end(), slots, slots + S);
+    }
+};
+}  // namespace
+
+int hnswb200_graph::upload_full() {
+    if (ctx->use()) return HNSWB200_ECUDA;
+    free_device();
+    chains0.clear();
+    chainsu.clear();
+    chain0_used = chainu_used = 0;
+    const uint64_t n = h.n_points();
+    // leave head-room so appended points / new continuation rows do not force a rebuild
+    rows0_cap = n + n / 8 + 1024;
+    chain0_cap = std::max<uint64_t>(1024, h.a0.spill.size() * 2 + n / 256);
+    rowsu_cap = h.au.rows() + h.au.rows() / 8 + 1024;
+    chainu_cap = std::max<uint64_t>(1024, h.au.spill.size() * 2 + h.au.rows() / 256);
+    upper_off_cap = rows0_cap;
+    const uint32_t S0 = h.a0.S, SU = h.au.S;
+    std::vector<uint32_t> st0((rows0_cap + chain0_cap) * S0, hb::H_EMPTY);
+    {
+        VecSink sink(st0, S0);
+        for (uint64_t r = 0; r < n; ++r)
+            if (!materialise_row(h.a0, (uint32_t)r, rows0_cap, chain0_cap, chain0_used, chains0, sink))
+                return fail(HNSWB200_ENOMEM, "graph: continuation rows exhausted");
+    }
+    std::vector<uint32_t> stu((rowsu_cap + chainu_cap) * SU, hb::H_EMPTY);
+    {
+        VecSink sink(stu, SU);
+        for (uint64_t r = 0; r < h.au.rows(); ++r)
+            if (!materialise_row(h.au, (uint32_t)r, rowsu_cap, chainu_cap, chainu_used, chainsu, sink))
+                return fail(HNSWB200_ENOMEM, "graph: continuation rows exhausted");
+    }
+    std::vector<uint32_t> uo(upper_off_cap, hb::H_EMPTY);
+    std::copy(h.upper_off.begin(), h.upper_off.end(), uo.begin());
+    HB_CUDA(cudaMalloc((void**)&d_adj0, st0.size() * 4));
+    HB_CUDA(cudaMalloc((void**)&d_adju, stu.size() * 4));
+    HB_CUDA(cudaMalloc((void**)&d_upper_off, uo.size() * 4));
+    HB_CUDA(cudaMemcpyAsync(d_adj0, st0.data(), st0.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    HB_CUDA(cudaMemcpyAsync(d_adju, stu.data(), stu.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    HB_CUDA(cudaMemcpyAsync(d_upper_off, uo.data(), uo.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    HB_CUDA(cudaStreamSynchronize(ctx->stream));
+    device_valid = true;
+    return 0;
+}
+
+int hnswb200_graph::sync_new_nodes(uint64_t first_new) {
+    if (!device_valid || h.n_points() > rows0_cap || h.au.rows() > rowsu_cap || h.n_points() > upper_off_cap)
+        return upload_full();
+    if (ctx->use()) return HNSWB200_ECUDA;
+    // rows past the old end are already EMPTY on the device; only upper_off is new
+    uint64_t cnt = h.n_points() - first_new;
+    if (cnt) {
+        HB_CUDA(cudaMemcpyAsync(d_upper_off + first_new, h.upper_off.data() + first_new, cnt * 4,
+                                cudaMemcpyHostToDevice, ctx->stream));
+        HB_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    return 0;
+}
+
+int hnswb200_graph::upload_rows(std::vector<uint32_t>& dirty0, std::vector<uint32_t>& dirtyu) {
+    if (!device_valid || h.n_points() > rows0_cap || h.au.rows() > rowsu_cap) {
+        dirty0.clear();
+        dirtyu.clear();
+        return upload_full();
+    }
+    if (ctx->use()) return HNSWB200_ECUDA;
+    for (int which = 0; which < 2; ++which) {
+        std::vector<uint32_t>& dirty = which ? dirtyu : dirty0;
+        if (dirty.empty()) continue;
+        std::sort(dirty.begin(), dirty.end());
+        dirty.erase(std::unique(dirty.begin(), dirty.end()), dirty.end());
+        const hb::AdjStore& s = which ? h.au : h.a0;
+        std::vector<uint32_t> rows, data;
+        ListSink sink(rows, data, s.S);
+        bool ok = true;
+        for (uint32_t r : dirty) {
+            ok = which ? materialise_row(s, r, rowsu_cap, chainu_cap, chainu_used, chainsu, sink)
+                       : materialise_row(s, r, rows0_cap, chain0_cap, chain0_used, chains0, sink);
+            if (!ok) break;
+        }
+        if (!ok) {  // out of continuation rows: rebuild with more head-room
+            dirty0.clear();
+            dirtyu.clear();
+            return upload_full();
+        }
+        hb::DevBuf<uint32_t> d_rows, d_data;
+        HB_CUDA(d_rows.alloc(rows.size()));
+        HB_CUDA(d_data.alloc(data.size()));
+        HB_CUDA(cudaMemcpyAsync(d_rows.p, rows.data(), rows.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+        HB_CUDA(cudaMemcpyAsync(d_data.p, data.data(), data.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+        HB_CUDA(hb::launch_scatter_rows(which ? d_adju : d_adj0, s.S, d_rows.p, d_data.p, (uint32_t)rows.size(),
+                                        ctx->stream));
+        HB_CUDA(cudaStreamSynchronize(ctx->stream));
+        dirty.clear();
+    }
+    return 0;
+}
+
+extern "C" {
+
+int hnswb200_graph_upload(hnswb200_ctx* c, uint64_t n_points, uint32_t n_layers, const uint32_t* caps,
+                          const uint64_t* n_nodes, const uint32_t* const* node_ids,
+                          const uint64_t* const* offsets, const uint32_t* const* nbrs,
+                          hnswb200_graph** out) {
+    if (!c || !out || !caps || !n_nodes || !node_ids || !offsets || !nbrs)
+        return fail(HNSWB200_EINVAL, "graph_upload: NULL argument");
+    if (n_layers == 0) return fail(HNSWB200_EINVAL, "graph_upload: an index has at least one layer");
+    if (n_points >= (1ull << 31)) return fail(HNSWB200_EINVAL, "graph_upload: more than 2^31-1 points");
+    for (uint32_t l = 2; l < n_layers; ++l)
+        if (caps[l] != caps[1]) return fail(HNSWB200_EINVAL, "graph_upload: upper layers must share one cap (Layers::add_level)");
+    if (n_nodes[0] != n_points) return fail(HNSWB200_EINVAL, "graph_upload: layer 0 must hold every point");
+    // level of a node = highest layer that lists it; membership must be nested
+    std::vector<int> lvl(n_points, -1);
+    for (uint32_t l = 0; l < n_layers; ++l) {
+        for (uint64_t r = 0; r < n_nodes[l]; ++r) {
+            uint32_t id = node_ids[l][r];
+            if (id >= n_points) return fail(HNSWB200_EINVAL, "graph_upload: node id out of range");
+            if (lvl[id] != (int)l - 1) return fail(HNSWB200_EINVAL, "graph_upload: layer membership is not nested / node listed twice");
+            lvl[id] = (int)l;
+        }
+    }
+    hnswb200_graph* g = new hnswb200_graph();
+    g->ctx = c;
+    uint32_t capu = n_layers > 1 ? caps[1] : (caps[0] + 1) / 2;
+    g->h.init(capu, caps[0], capu);
+    for (uint64_t i = 0; i < n_points; ++i) g->h.add_node((uint32_t)lvl[i]);
+    while (g->h.layer_nodes.size() < n_layers) g->h.layer_nodes.push_back(0);
+    for (uint32_t l = 0; l < n_layers; ++l) {
+        hb::AdjStore& s = g->h.store(l);
+        for (uint64_t r = 0; r < n_nodes[l]; ++r) {
+            uint32_t id = node_ids[l][r];
+            uint32_t row = g->h.row(id, l);
+            for (uint64_t e = offsets[l][r]; e < offsets[l][r + 1]; ++e) {
+                uint32_t nb = nbrs[l][e];
+                if (nb >= n_points || !g->h.in_layer(nb, l)) {
+                    delete g;
+                    return fail(HNSWB200_EINVAL, "graph_upload: neighbour is not a node of the layer (NodeNotInGraph)");
+                }
+                if (nb == id) { delete g; return fail(HNSWB200_EINVAL, "graph_upload: self connection"); }
+                s.insert(row, nb);
+            }
+        }
+    }
+    g->h.weights_valid = false;  // edge lengths are recomputed on the device if the index is extended
+    int rc = g->upload_full();
+    if (rc) { hnswb200_graph_destroy(g); return rc; }
+    *out = g;
+    return 0;
+}
+
+uint32_t hnswb200_graph_nb_layers(const hnswb200_graph* g) { return g ? g->h.n_layers() : 0; }
+uint64_t hnswb200_graph_layer_nb_nodes(const hnswb200_graph* g, uint32_t l) {
+    return (g && l < g->h.n_layers()) ? g->h.layer_nodes[l] : 0;
+}
+uint64_t hnswb200_graph_layer_nb_edges(const hnswb200_graph* g, uint32_t l) {
+    if (!g || l >= g->h.n_layers()) return 0;
+    uint64_t e = 0;
+    for (uint64_t i = 0; i < g->h.n_points(); ++i)
+        if (g->h.level[i] >= l) e += g->h.degree((uint32_t)i, l);
+    return e;
+}
+uint32_t hnswb200_graph_layer_cap(const hnswb200_graph* g, uint32_t l) { return g ? g->h.cap(l) : 0; }
+
+int hnswb200_graph_export_layer(const hnswb200_graph* g, uint32_t l, uint32_t* node_ids, uint64_t* offsets,
+                                uint32_t* nbrs) {
+    if (!g || l >= g->h.n_layers()) return fail(HNSWB200_EINVAL, "graph_export_layer: Layer not found in the structure.");
+    uint64_t r = 0, off = 0;
+    std::vector<uint32_t> tmp;
+    for (uint64_t i = 0; i < g->h.n_points(); ++i) {
+        if (g->h.level[i] < l) continue;
+        if (node_ids) node_ids[r] = (uint32_t)i;
+        if (offsets) offsets[r] = off;
+        g->h.store(l).list(g->h.row((uint32_t)i, l), tmp);
+        std::sort(tmp.begin(), tmp.end());
+        if (nbrs) for (uint32_t v : tmp) nbrs[off++] = v;
+        else off += tmp.size();
+        ++r;
+    }
+    if (offsets) offsets[r] = off;
+    return 0;
+}
+
+void hnswb200_graph_destroy(hnswb200_graph* g) {
+    if (!g) return;
+    g->free_device();
+    delete g;
+}
+
+// ---------------------------------------------------------------------------
+// index
+// ---------------------------------------------------------------------------
+int hnswb200_index_from_parts(hnswb200_ctx* c, hnswb200_points* points, hnswb200_graph* graph,
+                              const hnswb200_params* params, hnswb200_index** out) {
+    if (!c || !points || !graph || !params || !out) return fail(HNSWB200_EINVAL, "index_from_parts: NULL argument");
+    if (points->n != graph->h.n_points()) return fail(HNSWB200_EINVAL, "index_from_parts: points and graph disagree on the number of points");
+    if (params->dim != points->L.dim) return fail(HNSWB200_EINVAL, "index_from_parts: params.dim != points dimension");
+    if (points->n && params->ep >= points->n) return fail(HNSWB200_EINVAL, "index_from_parts: entry point out of range");
+    if (points->n && graph->h.level[params->ep] + 1u != graph->h.n_layers())
+        return fail(HNSWB200_EINVAL, "index_from_parts: entry point is not a node of the top layer");
+    hnswb200_index* ix = new hnswb200_index();
+    ix->ctx = c;
+    ix->points = points;
+    ix->graph = graph;
+    ix->params = *params;
+    *out = ix;
+    return 0;
+}
+
+void hnswb200_index_destroy(hnswb200_index* ix) {
+    if (!ix) return;
+    hnswb200_points_destroy(ix->points);
+    hnswb200_graph_destroy(ix->graph);
+    delete ix;
+}
+int hnswb200_index_params(const hnswb200_index* ix, hnswb200_params* out) {
+    if (!ix || !out) return fail(HNSWB200_EINVAL, "index_params: NULL argument");
+    *out = ix->params;
+    return 0;
+}
+uint64_t hnswb200_index_len(const hnswb200_index* ix) { return ix ? ix->points->n : 0; }
+const hnswb200_points* hnswb200_index_points(const hnswb200_index* ix) { return ix ? ix->points : nullptr; }
+const hnswb200_graph* hnswb200_index_graph(const hnswb200_index* ix) { return ix ? ix->graph : nullptr; }
+
+// ---------------------------------------------------------------------------
+// search
+// ---------------------------------------------------------------------------
+static int search_check(const hnswb200_index* ix, uint64_t nq, uint32_t n, uint32_t ef) {
+    if (ix->points->n == 0) return fail(HNSWB200_ESTATE, "search: the index holds no points");
+    if (n == 0 || ef == 0) return fail(HNSWB200_EINVAL, "search: n and ef must be >= 1");
+    if (nq >= (1ull << 32)) return fail(HNSWB200_EINVAL, "search: too many queries in one call");
+    if (ef > 16384) return fail(HNSWB200_EINVAL, "search: ef above 16384 is not supported by the shared-memory result list");
+    if (!ix->graph->device_valid) return fail(HNSWB200_ESTATE, "search: graph is not resident on the device");
+    return 0;
+}
+
+int hnswb200_search_dev(hnswb200_ctx* c, const hnswb200_index* ix, const float* d_queries, uint64_t nq,
+                        uint32_t n, uint32_t ef, uint32_t* d_out_ids, float* d_out_dists,
+                        uint32_t* d_out_counts, uint32_t* d_hops, uint32_t* d_evals, uint32_t* d_flags,
+                        uint32_t* d_nbrs) {
+    if (!c || !ix || (nq && (!d_queries || !d_out_ids))) return fail(HNSWB200_EINVAL, "search_dev: NULL argument");
+    if (nq == 0) return 0;
+    int rc = search_check(ix, nq, n, ef);
+    if (rc) return rc;
+    if (c->use()) return HNSWB200_ECUDA;
+    SearchLaunch a;
+    a.rec = ix->points->d_rec;
+    a.L = ix->points->L;
+    a.g = ix->graph->view();
+    a.ep = ix->params.ep;
+    a.queries = d_queries;
+    a.nq = (uint32_t)nq;
+    a.topn = n;
+    a.ef = ef;
+    a.vis_slots = 0;
+    a.out_ids = d_out_ids;
+    a.out_dists = d_out_dists;
+    a.out_counts = d_out_counts;
+    a.out_hops = d_hops;
+    a.out_evals = d_evals;
+    a.out_flags = d_flags;
+    a.out_nbrs = d_nbrs;
+    a.work_counter = c->d_scratch;
+    HB_CUDA(launch_search(a, c->num_sms, c->stream));
+    return 0;
+}
+
+int hnswb200_search(hnswb200_ctx* c, const hnswb200_index* ix, const float* queries, uint64_t nq,
+                    uint32_t dim, uint32_t n, uint32_t ef, uint32_t* out_ids, float* out_dists,
+                    uint32_t* out_counts, const hnswb200_search_stats* stats) {
+    if (!c || !ix || (nq && (!queries || !out_ids))) return fail(HNSWB200_EINVAL, "search: NULL argument");
+    if (dim != ix->points->L.dim)
+        return fail(HNSWB200_EINVAL, "search: query dimension " + std::to_string(dim) + " != index dimension " +
+                                         std::to_string(ix->points->L.dim));
+    if (nq == 0) return 0;
+    int rc = search_check(ix, nq, n, ef);
+    if (rc) return rc;
+    if (c->use()) return HNSWB200_ECUDA;
+    // grow-only per-context workspace: no cudaMalloc on the steady-state query path
+    const size_t b_q = nq * dim * 4, b_ids = nq * (size_t)n * 4, b_u = nq * 4;
+    auto al = [](size_t v) { return (v + 255) / 256 * 256; };
+    size_t total = al(b_q) + 2 * al(b_ids) + 5 * al(b_u);
+    if (c->ws_reserve(total)) return HNSWB200_ECUDA;
+    unsigned char* w = (unsigned char*)c->d_ws;
+    float* dq = (float*)w; w += al(b_q);
+    uint32_t* dids = (uint32_t*)w; w += al(b_ids);
+    float* dd = (float*)w; w += al(b_ids);
+    uint32_t* dcnt = (uint32_t*)w; w += al(b_u);
+    uint32_t* dhops = (uint32_t*)w; w += al(b_u);
+    uint32_t* devals = (uint32_t*)w; w += al(b_u);
+    uint32_t* dflags = (uint32_t*)w; w += al(b_u);
+    uint32_t* dnbrs = (uint32_t*)w;
+    HB_CUDA(cudaMemcpyAsync(dq, queries, b_q, cudaMemcpyHostToDevice, c->stream));
+    rc = hnswb200_search_dev(c, ix, dq, nq, n, ef, dids, dd, dcnt, dhops, devals, dflags, dnbrs);
+    if (rc) return rc;
+    if (c->h_flags.size() < nq) c->h_flags.resize(nq);
+    uint32_t* flags = c->h_flags.data();
+    HB_CUDA(cudaMemcpyAsync(out_ids, dids, b_ids, cudaMemcpyDeviceToHost, c->stream));
+    if (out_dists) HB_CUDA(cudaMemcpyAsync(out_dists, dd, b_ids, cudaMemcpyDeviceToHost, c->stream));
+    if (out_counts) HB_CUDA(cudaMemcpyAsync(out_counts, dcnt, b_u, cudaMemcpyDeviceToHost, c->stream));
+    if (stats && stats->hops) HB_CUDA(cudaMemcpyAsync(stats->hops, dhops, b_u, cudaMemcpyDeviceToHost, c->stream));
+    if (stats && stats->evals) HB_CUDA(cudaMemcpyAsync(stats->evals, devals, b_u, cudaMemcpyDeviceToHost, c->stream));
+    if (stats && stats->nbrs) HB_CUDA(cudaMemcpyAsync(stats->nbrs, dnbrs, b_u, cudaMemcpyDeviceToHost, c->stream));
+    HB_CUDA(cudaMemcpyAsync(flags, dflags, b_u, cudaMemcpyDeviceToHost, c->stream));
+    HB_CUDA(cudaStreamSynchronize(c->stream));
+    if (stats && stats->flags) memcpy(stats->flags, flags, b_u);
+    for (uint64_t i = 0; i < nq; ++i)
+        if (flags[i] & 1u) return fail(HNSWB200_EINVAL, "search: NaN in query " + std::to_string(i) + " (the reference panics in partial_cmp().unwrap())");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// brute force
+// ---------------------------------------------------------------------------
+int hnswb200_bruteforce_topk_dev(hnswb200_ctx* c, const hnswb200_points* base, const float* d_queries,
+                                 uint64_t nq, uint32_t k, uint32_t id_offset, uint32_t* d_out_ids,
+                                 float* d_out_dists) {
+    if (!c || !base || (nq && (!d_queries || !d_out_ids))) return fail(HNSWB200_EINVAL, "bruteforce: NULL argument");
+    if (k == 0 || k > 2048) return fail(HNSWB200_EINVAL, "bruteforce: k must be in 1..2048");
+    if (nq == 0) return 0;
+    if (nq >= (1ull << 31)) return fail(HNSWB200_EINVAL, "bruteforce: too many queries");
+    if (c->use()) return HNSWB200_ECUDA;
+    const RecLayout& L = base->L;
+    const uint32_t cap = 2048;
+    DevBuf<uint8_t> qrec;
+    DevBuf<uint64_t> topk, tau, buf;
+    DevBuf<uint32_t> cnt;
+    HB_CUDA(qrec.alloc(nq * L.stride));
+    HB_CUDA(topk.alloc(nq * k));
+    HB_CUDA(tau.alloc(nq));
+    HB_CUDA(buf.alloc(nq * cap));
+    HB_CUDA(cnt.alloc(nq));
+    uint32_t* nan_flag = c->d_scratch + 1;
+    uint32_t* ovf_flag = c->d_scratch + 2;
+    HB_CUDA(cudaMemsetAsync(nan_flag, 0, 8, c->stream));
+    HB_CUDA(cudaMemsetAsync(qrec.p, 0, nq * L.stride, c->stream));
+    HB_CUDA(cudaMemsetAsync(topk.p, 0xFF, nq * k * 8, c->stream));
+    HB_CUDA(cudaMemsetAsync(tau.p, 0xFF, nq * 8, c->stream));
+    HB_CUDA(cudaMemsetAsync(cnt.p, 0, nq * 4, c->stream));
+    // queries are quantised like points (Point::new) and laid out as records
+    HB_CUDA(launch_quantise(d_queries, nq, L, qrec.p, nullptr, nullptr, nullptr, nan_flag, c->stream));
+    uint32_t flags[2] = {0, 0};
+    HB_CUDA(cudaMemcpyAsync(flags, nan_flag, 8, cudaMemcpyDeviceToHost, c->stream));
+    HB_CUDA(cudaStreamSynchronize(c->stream));
+    if (flags[0]) return fail(HNSWB200_EINVAL, "bruteforce: NaN in a query");
+    // Chunks double in size: with tau = current k-th best, the expected number of survivors of a
+    // chunk as large as everything seen before is <= k per query.  A chunk that overflows the
+    // per-query buffer (adversarial order) is redone in pieces of `cap` rows, which cannot overflow.
+    const uint64_t N = base->n, MAXCH = 1ull << 18;
+    uint64_t done = 0;
+    while (done < N) {
+        uint64_t ch = done == 0 ? std::min<uint64_t>(cap, N) : std::min<uint64_t>(std::min<uint64_t>(done, MAXCH), N - done);
+        HB_CUDA(launch_bf_chunk(base->d_rec, L, done, done + ch, id_offset, qrec.p, (uint32_t)nq, tau.p, buf.p,
+                                cap, cnt.p, ovf_flag, c->stream));
+        uint32_t ovf = 0;
+        HB_CUDA(cudaMemcpyAsync(&ovf, ovf_flag, 4, cudaMemcpyDeviceToHost, c->stream));
+        HB_CUDA(cudaStreamSynchronize(c->stream));
+        if (ovf) {
+            HB_CUDA(cudaMemsetAsync(ovf_flag, 0, 4, c->stream));
+            HB_CUDA(cudaMemsetAsync(cnt.p, 0, nq * 4, c->stream));
+            for (uint64_t s = done; s < done + ch; s += cap) {
+                uint64_t e = std::min<uint64_t>(s + cap, done + ch);
+                HB_CUDA(launch_bf_chunk(base->d_rec, L, s, e, id_offset, qrec.p, (uint32_t)nq, tau.p, buf.p, cap,
+                                        cnt.p, ovf_flag, c->stream));
+                HB_CUDA(launch_bf_merge(topk.p, k, tau.p, buf.p, cap, cnt.p, (uint32_t)nq, c->stream));
+            }
+        } else {
+            HB_CUDA(launch_bf_merge(topk.p, k, tau.p, buf.p, cap, cnt.p, (uint32_t)nq, c->stream));
+        }
+        done += ch;
+    }
+    HB_CUDA(launch_keys_to_out(topk.p, k, (uint32_t)nq, d_out_ids, d_out_dists, c->stream));
+    HB_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int hnswb200_bruteforce_topk(hnswb200_ctx* c, const hnswb200_points* base, const float* queries,
+                             uint64_t nq, uint32_t k, uint32_t id_offset, uint32_t* out_ids,
+                             float* out_dists) {
+    if (!c || !base || (nq && (!queries || !out_ids))) return fail(HNSWB200_EINVAL, "bruteforce: NULL argument");
+    if (nq == 0) return 0;
+    if (c->use()) return HNSWB200_ECUDA;
+    DevBuf<float> dq, dd;
+    DevBuf<uint32_t> dids;
+    HB_CUDA(dq.alloc(nq * base->L.dim));
+    HB_CUDA(dids.alloc(nq * k));
+    HB_CUDA(dd.alloc(nq * k));
+    HB_CUDA(cudaMemcpyAsync(dq.p, queries, nq * base->L.dim * 4, cudaMemcpyHostToDevice, c->stream));
+    int rc = hnswb200_bruteforce_topk_dev(c, base, dq.p, nq, k, id_offset, dids.p, dd.p);
+    if (rc) return rc;
+    HB_CUDA(cudaMemcpyAsync(out_ids, dids.p, nq * k * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (out_dists) HB_CUDA(cudaMemcpyAsync(out_dists, dd.p, nq * k * 4, cudaMemcpyDeviceToHost, c->stream));
+    HB_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// top-k merge
+// ---------------------------------------------------------------------------
+int hnswb200_topk_merge_dev(hnswb200_ctx* c, const uint32_t* d_ids, const float* d_dists, uint32_t G,
+                            uint64_t nq, uint32_t k, uint32_t* d_out_ids, float* d_out_dists) {
+    if (!c || !d_ids || !d_dists || !d_out_ids) return fail(HNSWB200_EINVAL, "topk_merge: NULL argument");
+    if (G == 0 || k == 0 || (uint64_t)G * k > 16384) return fail(HNSWB200_EINVAL, "topk_merge: need 1 <= G*k <= 16384");
+    if (c->use()) return HNSWB200_ECUDA;
+    HB_CUDA(launch_topk_merge(d_ids, d_dists, G, (uint32_t)nq, k, d_out_ids, d_out_dists, c->stream));
+    return 0;
+}
+
+int hnswb200_topk_merge(hnswb200_ctx* c, const uint32_t* ids, const float* dists, uint32_t G, uint64_t nq,
+                        uint32_t k, uint32_t* out_ids, float* out_dists) {
+    if (!c || !ids || !dists || !out_ids) return fail(HNSWB200_EINVAL, "topk_merge: NULL argument");
+    if (nq == 0) return 0;
+    if (c->use()) return HNSWB200_ECUDA;
+    uint64_t tot = (uint64_t)G * nq * k;
+    DevBuf<uint32_t> di, doi;
+    DevBuf<float> dd, dod;
+    HB_CUDA(di.alloc(tot));
+    HB_CUDA(dd.alloc(tot));
+    HB_CUDA(doi.alloc(nq * k));
+    HB_CUDA(dod.alloc(nq * k));
+    HB_CUDA(cudaMemcpyAsync(di.p, ids, tot * 4, cudaMemcpyHostToDevice, c->stream));
+    HB_CUDA(cudaMemcpyAsync(dd.p, dists, tot * 4, cudaMemcpyHostToDevice, c->stream));
+    int rc = hnswb200_topk_merge_dev(c, di.p, dd.p, G, nq, k, doi.p, dod.p);
+    if (rc) return rc;
+    HB_CUDA(cudaMemcpyAsync(out_ids, doi.p, nq * k * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (out_dists) HB_CUDA(cudaMemcpyAsync(out_dists, dod.p, nq * k * 4, cudaMemcpyDeviceToHost, c->stream));
+    HB_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// HNSW::save / HNSW::load byte formats (all big-endian)
+// ---------------------------------------------------------------------------
+}  // extern "C"
+
+namespace {
+void put_u64(std::vector<uint8_t>& b, uint64_t v) { for (int i = 7; i >= 0; --i) b.push_back((uint8_t)(v >> (8 * i))); }
+void put_u32(std::vector<uint8_t>& b, uint32_t v) { for (int i = 3; i >= 0; --i) b.push_back((uint8_t)(v >> (8 * i))); }
+void put_f32(std::vector<uint8_t>& b, float f) { uint32_t u; memcpy(&u, &f, 4); put_u32(b, u); }
+uint64_t get_u64(const uint8_t* p) { uint64_t v = 0; for (int i = 0; i < 8; ++i) v = (v << 8) | p[i]; return v; }
+uint32_t get_u32(const uint8_t* p) { uint32_t v = 0; for (int i = 0; i < 4; ++i) v = (v << 8) | p[i]; return v; }
+float get_f32(const uint8_t* p) { uint32_t u = get_u32(p); float f; memcpy(&f, &u, 4); return f; }
+bool write_file(const std::string& path, const std::vector<uint8_t>& b) {
+    FILE* f = fopen(path.c_str(), "wb");
+    if (!f) return false;
+    size_t w = b.empty() ? 0 : fwrite(b.data(), 1, b.size(), f);
+    fclose(f);
+    return w == b.size();
+}
+bool read_file(const std::string& path, std::vector<uint8_t>& b) {
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    fseek(f, 0, SEEK_END);
+    long sz = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    b.resize((size_t)sz);
+    size_t r = sz ? fread(b.data(), 1, (size_t)sz, f) : 0;
+    fclose(f);
+    return r == (size_t)sz;
+}
+}  // namespace
+
+extern "C" {
+
+int hnswb200_index_save_dir(hnswb200_ctx* c, const hnswb200_index* ix, const char* dir) {
+    if (!c || !ix || !dir) return fail(HNSWB200_EINVAL, "save: NULL argument");
+    const hnswb200_points* P = ix->points;
+    const uint64_t n = P->n, dim = P->L.dim;
+    if (n == 0) return fail(HNSWB200_ESTATE, "save: the index holds no points");
+    std::string d(dir);
+    if (mkdir(d.c_str(), 0777) != 0 && errno != EEXIST) return fail(HNSWB200_EIO, "Could not create dir " + d);
+    std::vector<uint8_t> codes(n * dim), levels(n);
+    std::vector<float> mins(n), deltas(n);
+    int rc = hnswb200_points_download(c, P, codes.data(), mins.data(), deltas.data(), levels.data());
+    if (rc) return rc;
+    // points file: points.rs:119-131, point.rs:55-61, quant.rs:102-110 (min before delta)
+    std::vector<uint8_t> b;
+    b.reserve(16 + n * (9 + dim));
+    put_u64(b, n);
+    put_u64(b, 9 + dim);
+    for (uint64_t i = 0; i < n; ++i) {
+        b.push_back(levels[i]);
+        put_f32(b, mins[i]);
+        put_f32(b, deltas[i]);
+        b.insert(b.end(), &codes[i * dim], &codes[(i + 1) * dim]);
+    }
+    if (!write_file(d + "/points", b)) return fail(HNSWB200_EIO, "Could not write bytes to point file");
+    b.clear();  // params.rs:78-91
+    put_u64(b, ix->params.m); put_u64(b, ix->params.mmax); put_u64(b, ix->params.mmax0);
+    put_f32(b, ix->params.ml);
+    put_u64(b, ix->params.ef_cons); put_u64(b, ix->params.dim); put_u64(b, ix->params.ep);
+    if (!write_file(d + "/params", b)) return fail(HNSWB200_EIO, "Could not write bytes to params file");
+    if (mkdir((d + "/layers").c_str(), 0777) != 0 && errno != EEXIST) return fail(HNSWB200_EIO, "Could not create layers dir");
+    const hb::HostGraph& h = ix->graph->h;
+    std::vector<uint32_t> tmp;
+    for (uint32_t l = 0; l < h.n_layers(); ++l) {  // graph.rs:165-219
+        // The reference pads rows to `m` words but never truncates; a node above the cap
+        // (possible) would misalign the file.  Keep it self-consistent:
+        // the row width in the header is max(cap, max degree).
+        uint32_t width = h.cap(l);
+        for (uint64_t i = 0; i < n; ++i)
+            if (h.level[i] >= l) width = std::max(width, h.degree((uint32_t)i, l));
+        if (width > 0xFFFF) return fail(HNSWB200_EIO, "save: degree does not fit the u16 row width");
+        b.clear();
+        b.push_back((uint8_t)l);
+        put_u32(b, (uint32_t)h.layer_nodes[l]);
+        b.push_back((uint8_t)(width >> 8));
+        b.push_back((uint8_t)width);
+        for (uint64_t i = 0; i < n; ++i) {
+            if (h.level[i] < l) continue;
+            put_u32(b, (uint32_t)i);
+            h.store(l).list(h.row((uint32_t)i, l), tmp);
+            for (uint32_t v : tmp) put_u32(b, v);
+            for (size_t j = tmp.size(); j < width; ++j) put_u32(b, 0xFFFFFFFFu);
+        }
+        if (!write_file(d + "/layers/" + std::to_string(l), b)) return fail(HNSWB200_EIO, "Could not write bytes to layer file");
+    }
+    return 0;
+}
+
+int hnswb200_index_load_dir(hnswb200_ctx* c, const char* dir, hnswb200_index** out) {
+    if (!c || !dir || !out) return fail(HNSWB200_EINVAL, "load: NULL argument");
+    std::string d(dir);
+    struct stat st;
+    if (stat(d.c_str(), &st) != 0) return fail(HNSWB200_EIO, "\"" + d + "\" does not exist");
+    std::vector<uint8_t> b;
+    if (!read_file(d + "/points", b) || b.size() < 16) return fail(HNSWB200_EIO, "Problem reading points file");
+    uint64_t n = get_u64(&b[0]), psz = get_u64(&b[8]);
+    if (psz < 10 || b.size() < 16 + n * psz) return fail(HNSWB200_EIO, "points file is truncated");
+    uint64_t dim = psz - 9;
+    std::vector<uint8_t> codes(n * dim), levels(n);
+    std::vector<float> mins(n), deltas(n);
+    for (uint64_t i = 0; i < n; ++i) {
+        const uint8_t* p = &b[16 + i * psz];
+        levels[i] = p[0];
+        mins[i] = get_f32(p + 1);
+        deltas[i] = get_f32(p + 5);
+        memcpy(&codes[i * dim], p + 9, dim);
+    }
+    if (!read_file(d + "/params", b) || b.size() < 52) return fail(HNSWB200_EIO, "Problem reading params file");
+    hnswb200_params prm;
+    prm.m = get_u64(&b[0]); prm.mmax = get_u64(&b[8]); prm.mmax0 = get_u64(&b[16]);
+    prm.ml = get_f32(&b[24]);
+    prm.ef_cons = get_u64(&b[28]); prm.dim = get_u64(&b[36]); prm.ep = (uint32_t)get_u64(&b[44]);
+    if (prm.dim != dim) return fail(HNSWB200_EIO, "params.dim does not match the point size");
+    // layers/<idx>, sorted numerically (template.rs:103-109)
+    std::vector<uint64_t> idxs;
+    DIR* dd = opendir((d + "/layers").c_str());
+    if (!dd) return fail(HNSWB200_EIO, "There was a problem reading layers");
+    while (dirent* e = readdir(dd)) {
+        if (e->d_name[0] == '.') continue;
+        idxs.push_back(strtoull(e->d_name, nullptr, 10));
+    }
+    closedir(dd);
+    std::sort(idxs.begin(), idxs.end());
+    uint32_t nl = (uint32_t)idxs.size();
+    if (nl == 0) return fail(HNSWB200_EIO, "index has no layer files");
+    std::vector<std::vector<uint32_t>> ids(nl), nb(nl);
+    std::vector<std::vector<uint64_t>> off(nl);
+    std::vector<uint32_t> caps(nl);
+    std::vector<uint64_t> nn(nl);
+    for (uint32_t l = 0; l < nl; ++l) {
+        if (!read_file(d + "/layers/" + std::to_string(idxs[l]), b) || b.size() < 7) return fail(HNSWB200_EIO, "Problem reading layer file");
+        if (b[0] != l) return fail(HNSWB200_EIO, "layer level does not match its position (template.rs:119)");
+        uint32_t cnt = get_u32(&b[1]);
+        uint32_t width = ((uint32_t)b[5] << 8) | b[6];
+        if (b.size() != 7 + (uint64_t)cnt * 4 * (width + 1))
+            return fail(HNSWB200_EIO, "layer file length != 7 + nb_nodes*4*(m+1): a row above the cap was written un-truncated by the reference (graph.rs:172-178)");
+        // cap as Layers::add_level makes it (layers.rs:50); equals `width` for reference-written files
+        caps[l] = std::min<uint32_t>(width, (uint32_t)(l == 0 ? 2 * prm.m : prm.m));
+        nn[l] = cnt;
+        std::vector<std::pair<uint32_t, std::vector<uint32_t>>> rows(cnt);
+        uint64_t o = 7;
+        for (uint32_t r = 0; r < cnt; ++r) {
+            rows[r].first = get_u32(&b[o]);
+            o += 4;
+            for (uint32_t j = 0; j < width; ++j) {
+                uint32_t v = get_u32(&b[o + 4 * j]);
+                if (v == 0xFFFFFFFFu) break;
+                rows[r].second.push_back(v);
+            }
+            o += 4ull * width;
+        }
+        off[l].push_back(0);
+        for (auto& r : rows) {
+            ids[l].push_back(r.first);
+            nb[l].insert(nb[l].end(), r.second.begin(), r.second.end());
+            off[l].push_back(nb[l].size());
+        }
+        if (nb[l].empty()) nb[l].push_back(0);
+    }
+    std::vector<const uint32_t*> pid(nl), pnb(nl);
+    std::vector<const uint64_t*> poff(nl);
+    for (uint32_t l = 0; l < nl; ++l) { pid[l] = ids[l].data(); pnb[l] = nb[l].data(); poff[l] = off[l].data(); }
+    hnswb200_points* P = nullptr;
+    hnswb200_graph* G = nullptr;
+    int rc = hnswb200_points_upload(c, codes.data(), mins.data(), deltas.data(), levels.data(), n, (uint32_t)dim, &P);
+    if (rc) return rc;
+    rc = hnswb200_graph_upload(c, n, nl, caps.data(), nn.data(), pid.data(), poff.data(), pnb.data(), &G);
+    if (rc) { hnswb200_points_destroy(P); return rc; }
+    rc = hnswb200_index_from_parts(c, P, G, &prm, out);
+    if (rc) { hnswb200_points_destroy(P); hnswb200_graph_destroy(G); }
+    return rc;
+}
+
+int64_t hnswb200_load_glove(const char* path, uint64_t lim, float* out, uint64_t cap, uint64_t* dim_out) {
+    FILE* f = fopen(path, "r");
+    if (!f) { set_error(std::string("cannot open ") + path); return HNSWB200_EIO; }
+    char* line = nullptr;
+    size_t lcap = 0;
+    int64_t rows = 0;
+    uint64_t dim = 0, w = 0;
+    while (getline(&line, &lcap, f) > 0) {
+        if (lim > 0 && (uint64_t)rows >= lim) break;
+        char* save = nullptr;
+        char* tok = strtok_r(line, " \n\r", &save);
+        if (!tok) continue;
+        uint64_t dcount = 0;
+        while ((tok = strtok_r(nullptr, " \n\r", &save))) {
+            char* end = nullptr;
+            float v = strtof(tok, &end);  // correctly rounded, like Rust's parse::<f32>()
+            if (end == tok || *end != '\0') continue;
+            if (out && w < cap) out[w] = v;
+            ++w;
+            ++dcount;
+        }
+        if (rows == 0) dim = dcount;
+        else if (dcount != dim) {
+            set_error("Line " + std::to_string(rows + 1) + ": vector is not the same size as others.");
+            free(line);
+            fclose(f);
+            return HNSWB200_EINVAL;
+        }
+        ++rows;
+    }
+    free(line);
+    fclose(f);
+    if (dim_out) *dim_out = dim;
+    return rows;
+}
+
+}  // extern "C"

@@ -1,0 +1,295 @@
+// Bit-exact quantised L2 distance primitives (device side).
+//
+// Arithmetic contract (reference vectors/src/quant.rs:14-37, 41-66):
+//   deq(c)  = fadd(fmul((f32)c, delta), min)            two roundings, never an FMA
+//   acc[j] += fmul(t, t), t = fsub(x, y)                 per residue j = i mod 8, increasing i
+//   remainder elements -> acc[0], after the chunks
+//   s = ((((((a0+a1)+a2)+a3)+a4)+a5)+a6)+a7 ; d = sqrt_rn(s)
+// A group of 4 lanes evaluates one record; lane l owns (acc[2l], acc[2l+1]) and
+// works on them as one packed f32x2 value (FADD2 on sm_100a).  Multiplications are
+// issued as scalar FMULs: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2
+// even with explicit rounding modifiers and --fmad=false, which would break the
+// contract; scalar mul.rn.f32 is never contracted (tools/check_sass.py verifies
+// that the built kernels contain no FFMA/FFMA2 in their distance loops).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "layout.h"
+
+typedef unsigned long long u64;
+#define HB_FULL 0xffffffffu
+
+namespace hb {
+
+__device__ __forceinline__ u64 pk(float a, float b) {
+    u64 r;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void up(u64 v, float& a, float& b) {
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ u64 add2(u64 a, u64 b) {
+    u64 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) {
+    u64 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+// exact u8 -> f32 for byte `b` (0..3) of word r: 0x4B0000bb = 2^23 + bb, minus 2^23 later
+__device__ __forceinline__ float magic_byte(uint32_t r, int b) {
+    return __uint_as_float(__byte_perm(r, 0x4B000000u, 0x7540u | (uint32_t)b));
+}
+__device__ __forceinline__ uint32_t word32(const uint4& w, int i) {
+    return i == 0 ? w.x : i == 1 ? w.y : i == 2 ? w.z : w.w;
+}
+
+// one chunk: record bytes (b0, b0+1) of register rr against the query pair q
+__device__ __forceinline__ u64 chunk_acc(u64 acc, uint32_t rr, int b0, float dl, u64 mn2, u64 q) {
+    const u64 magic = pk(8388608.0f, 8388608.0f);
+    u64 cf = sub2(pk(magic_byte(rr, b0), magic_byte(rr, b0 + 1)), magic);  // exact codes
+    float c0, c1;
+    up(cf, c0, c1);
+    u64 x = add2(pk(__fmul_rn(c0, dl), __fmul_rn(c1, dl)), mn2);
+    u64 t = sub2(x, q);
+    float t0, t1;
+    up(t, t0, t1);
+    return add2(acc, pk(__fmul_rn(t0, t0), __fmul_rn(t1, t1)));
+}
+__device__ __forceinline__ float rem_acc(float a0, float fm, float dl, float mn, float q) {
+    float c = __fadd_rn(fm, -8388608.0f);
+    float x = __fadd_rn(__fmul_rn(c, dl), mn);
+    float t = __fsub_rn(x, q);
+    return __fadd_rn(a0, __fmul_rn(t, t));
+}
+
+// sequential 8-way sum across the 4 lanes of a group; result broadcast to the group
+__device__ __forceinline__ float group_sum_sqrt(u64 acc, int gl, int gbase) {
+    float a0, a1;
+    up(acc, a0, a1);
+    float p = __fadd_rn(a0, a1);  // lane 0: (0 + a0) + a1 with 0 + a0 == a0
+    float t = __shfl_sync(HB_FULL, p, gbase + 0);
+    if (gl == 1) p = __fadd_rn(__fadd_rn(t, a0), a1);
+    t = __shfl_sync(HB_FULL, p, gbase + 1);
+    if (gl == 2) p = __fadd_rn(__fadd_rn(t, a0), a1);
+    t = __shfl_sync(HB_FULL, p, gbase + 2);
+    if (gl == 3) p = __fadd_rn(__fadd_rn(t, a0), a1);
+    p = __shfl_sync(HB_FULL, p, gbase + 3);
+    return __fsqrt_rn(p);
+}
+
+// ---------------------------------------------------------------------------
+// Query held in registers, dimension known at compile time (dim = 8*NCH + REM).
+// All 32 lanes of the warp must call dist() together (it shuffles).
+// ---------------------------------------------------------------------------
+template <int NCH, int REM>
+struct RegQuery {
+    static constexpr int W = (int)hb_layout_W(NCH);
+    static constexpr int TAIL = (int)hb_layout_tail(NCH, REM);
+    u64 q[NCH ? NCH : 1];
+    float qr[REM ? REM : 1];
+
+    // qd: dequantised query values in shared memory, natural element order
+    __device__ __forceinline__ void init(const RecLayout&, const float* qd, int gl) {
+#pragma unroll
+        for (int k = 0; k < NCH; ++k) {
+            float2 v = *reinterpret_cast<const float2*>(qd + 8 * k + 2 * gl);
+            q[k] = pk(v.x, v.y);
+        }
+#pragma unroll
+        for (int r = 0; r < REM; ++r) qr[r] = qd[8 * NCH + r];
+    }
+
+    __device__ __forceinline__ float dist(const uint8_t* __restrict__ rec, int gl, int gbase) const {
+        const uint4* p = reinterpret_cast<const uint4*>(rec);
+        uint4 w[W];
+#pragma unroll
+        for (int j = 0; j < W; ++j) w[j] = __ldg(p + 4 * j + gl);
+        uint4 tw = make_uint4(0, 0, 0, 0);
+        float mn, dl;
+        if (TAIL) {
+            tw = __ldg(p + 4 * W);
+            mn = __uint_as_float(tw.x);
+            dl = __uint_as_float(tw.y);
+        } else {
+            uint32_t last = w[W - 1].w;
+            mn = __uint_as_float(__shfl_sync(HB_FULL, last, gbase + 1));
+            dl = __uint_as_float(__shfl_sync(HB_FULL, last, gbase + 2));
+        }
+        const u64 mn2 = pk(mn, mn);
+        u64 acc = pk(0.0f, 0.0f);
+#pragma unroll
+        for (int k = 0; k < NCH; ++k) {
+            const int j = k / 8, c = k % 8;
+            acc = chunk_acc(acc, word32(w[j], c / 2), (c & 1) * 2, dl, mn2, q[k]);
+        }
+        if (REM > 0) {
+            float a0, a1;
+            up(acc, a0, a1);
+            float n0 = a0;
+#pragma unroll
+            for (int r = 0; r < REM; ++r) {
+                float fm;
+                if (TAIL) {
+                    const int bi = 8 + r;
+                    fm = magic_byte(word32(tw, bi / 4), bi % 4);
+                } else {
+                    const int pz = 2 * NCH + r, j = pz / 16, bi = pz % 16;
+                    fm = magic_byte(word32(w[j], bi / 4), bi % 4);
+                }
+                n0 = rem_acc(n0, fm, dl, mn, qr[r]);
+            }
+            acc = pk(gl == 0 ? n0 : a0, a1);
+        }
+        return group_sum_sqrt(acc, gl, gbase);
+    }
+};
+
+// ---------------------------------------------------------------------------
+// Query held in shared memory, runtime dimension (any dim).
+// ---------------------------------------------------------------------------
+struct SmemQuery {
+    const float* qd;
+    RecLayout L;
+    __device__ __forceinline__ void init(const RecLayout& l, const float* q, int) {
+        qd = q;
+        L = l;
+    }
+    __device__ __forceinline__ float dist(const uint8_t* __restrict__ rec, int gl, int gbase) const {
+        const uint4* p = reinterpret_cast<const uint4*>(rec);
+        const float mn = __ldg(reinterpret_cast<const float*>(rec + hb_min_offset(L)));
+        const float dl = __ldg(reinterpret_cast<const float*>(rec + hb_delta_offset(L)));
+        const u64 mn2 = pk(mn, mn);
+        u64 acc = pk(0.0f, 0.0f);
+        for (uint32_t j = 0; j < L.W; ++j) {
+            uint4 w = __ldg(p + 4 * j + gl);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                uint32_t k = 8 * j + c;
+                if (k < L.nch) {
+                    float2 v = *reinterpret_cast<const float2*>(qd + 8 * k + 2 * gl);
+                    acc = chunk_acc(acc, word32(w, c / 2), (c & 1) * 2, dl, mn2, pk(v.x, v.y));
+                }
+            }
+        }
+        if (L.rem) {
+            float a0, a1;
+            up(acc, a0, a1);
+            float n0 = a0;
+            for (uint32_t r = 0; r < L.rem; ++r) {
+                uint32_t byte = __ldg(rec + hb_code_offset(L, 8 * L.nch + r));
+                float fm = __uint_as_float(0x4B000000u | byte);
+                n0 = rem_acc(n0, fm, dl, mn, qd[8 * L.nch + r]);
+            }
+            acc = pk(gl == 0 ? n0 : a0, a1);
+        }
+        return group_sum_sqrt(acc, gl, gbase);
+    }
+};
+
+// record <-> record distance, both streamed from memory (Points::distance(a,b),
+// points/src/points.rs:86-93: x = a, y = b).  Runtime dimension.
+__device__ __forceinline__ float rec_rec_dist(const RecLayout& L, const uint8_t* __restrict__ ra,
+                                              const uint8_t* __restrict__ rb, int gl, int gbase) {
+    const uint4* pa = reinterpret_cast<const uint4*>(ra);
+    const uint4* pb = reinterpret_cast<const uint4*>(rb);
+    const float mna = __ldg(reinterpret_cast<const float*>(ra + hb_min_offset(L)));
+    const float dla = __ldg(reinterpret_cast<const float*>(ra + hb_delta_offset(L)));
+    const float mnb = __ldg(reinterpret_cast<const float*>(rb + hb_min_offset(L)));
+    const float dlb = __ldg(reinterpret_cast<const float*>(rb + hb_delta_offset(L)));
+    const u64 mna2 = pk(mna, mna);
+    const u64 magic = pk(8388608.0f, 8388608.0f);
+    u64 acc = pk(0.0f, 0.0f);
+    for (uint32_t j = 0; j < L.W; ++j) {
+        uint4 wa = __ldg(pa + 4 * j + gl);
+        uint4 wb = __ldg(pb + 4 * j + gl);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            uint32_t k = 8 * j + c;
+            if (k < L.nch) {
+                uint32_t rr = word32(wb, c / 2);
+                int b0 = (c & 1) * 2;
+                u64 cf = sub2(pk(magic_byte(rr, b0), magic_byte(rr, b0 + 1)), magic);
+                float c0, c1;
+                up(cf, c0, c1);
+                u64 y = add2(pk(__fmul_rn(c0, dlb), __fmul_rn(c1, dlb)), pk(mnb, mnb));
+                // t = x_a - y_b: negate the roles in chunk_acc by feeding y as the "query"
+                acc = chunk_acc(acc, word32(wa, c / 2), b0, dla, mna2, y);
+            }
+        }
+    }
+    if (L.rem) {
+        float a0, a1;
+        up(acc, a0, a1);
+        float n0 = a0;
+        for (uint32_t r = 0; r < L.rem; ++r) {
+            uint32_t off = hb_code_offset(L, 8 * L.nch + r);
+            float y = __fadd_rn(__fmul_rn((float)__ldg(rb + off), dlb), mnb);
+            float fm = __uint_as_float(0x4B000000u | (uint32_t)__ldg(ra + off));
+            n0 = rem_acc(n0, fm, dla, mna, y);
+        }
+        acc = pk(gl == 0 ? n0 : a0, a1);
+    }
+    return group_sum_sqrt(acc, gl, gbase);
+}
+
+// ---------------------------------------------------------------------------
+// Warp-level quantiser (QuantVec::new, vectors/src/quant.rs:41-66).
+// v: f32[dim] in global memory.  Writes the dequantised values to qd (shared or
+// global, natural order), optionally the codes, and returns min/delta.
+// Returns false if the vector holds a NaN (the reference panics).
+// max_by keeps the LAST of equal maxima, min_by the FIRST of equal minima.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ bool warp_quantise(const float* __restrict__ v, uint32_t dim, int lane,
+                                              float* qd, uint8_t* codes, float& mn_out,
+                                              float& dl_out) {
+    float mxv = -INFINITY, mnv = INFINITY;
+    int mxi = -1, mni = 0x7fffffff;
+    bool nan = false;
+    for (uint32_t i = lane; i < dim; i += 32) {
+        float x = v[i];
+        nan |= (x != x);
+        if (!(mxv > x)) { mxv = x; mxi = (int)i; }
+        if (x < mnv) { mnv = x; mni = (int)i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        float ov = __shfl_xor_sync(HB_FULL, mxv, o);
+        int oi = __shfl_xor_sync(HB_FULL, mxi, o);
+        if (ov > mxv || (ov == mxv && oi > mxi)) { mxv = ov; mxi = oi; }
+        ov = __shfl_xor_sync(HB_FULL, mnv, o);
+        oi = __shfl_xor_sync(HB_FULL, mni, o);
+        if (ov < mnv || (ov == mnv && oi < mni)) { mnv = ov; mni = oi; }
+    }
+    nan = __any_sync(HB_FULL, nan);
+    const float lb = mnv;
+    const float dl = __fdiv_rn(__fsub_rn(mxv, lb), 255.0f);
+    for (uint32_t i = lane; i < dim; i += 32) {
+        float b = __fadd_rn(__fdiv_rn(__fsub_rn(v[i], lb), dl), 0.5f);
+        float f = floorf(b);
+        f = fminf(fmaxf(f, 0.0f), 255.0f);  // Rust `as u8`: saturating, NaN -> 0
+        uint32_t c = (uint32_t)f;
+        if (codes) codes[i] = (uint8_t)c;
+        if (qd) qd[i] = __fadd_rn(__fmul_rn((float)c, dl), lb);
+    }
+    mn_out = lb;
+    dl_out = dl;
+    return !nan;
+}
+
+// dequantise a stored record into natural element order (qd[dim])
+__device__ __forceinline__ void warp_dequant_record(const RecLayout& L, const uint8_t* __restrict__ rec,
+                                                    int lane, float* qd) {
+    const float mn = __ldg(reinterpret_cast<const float*>(rec + hb_min_offset(L)));
+    const float dl = __ldg(reinterpret_cast<const float*>(rec + hb_delta_offset(L)));
+    for (uint32_t i = lane; i < L.dim; i += 32) {
+        uint32_t c = __ldg(rec + hb_code_offset(L, i));
+        qd[i] = __fadd_rn(__fmul_rn((float)c, dl), mn);
+    }
+}
+
+}  // namespace hb

@@ -1,0 +1,87 @@
+// Internal object model behind the opaque handles of include/hnsw_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/hnsw_b200.h"
+#include "hostgraph.h"
+#include "kernels.h"
+#include "layout.h"
+
+namespace hb {
+void set_error(const std::string& s);
+int cuda_fail(cudaError_t e, const char* what);
+template <class T>
+struct DevBuf {  // scoped device buffer
+    T* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t n) { return cudaMalloc((void**)&p, (n ? n : 1) * sizeof(T)); }
+};
+}  // namespace hb
+
+#define HB_CUDA(call)                                              \
+    do {                                                           \
+        cudaError_t _e = (call);                                   \
+        if (_e != cudaSuccess) return hb::cuda_fail(_e, #call);    \
+    } while (0)
+
+struct hnswb200_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int num_sms = 148;
+    uint32_t* d_scratch = nullptr;  // [0] work counter, [1] nan flag, [2] overflow flag, ...
+    void* d_ws = nullptr;           // grow-only workspace for the host-buffer entry points
+    size_t ws_bytes = 0;
+    std::vector<uint32_t> h_flags;
+    int ws_reserve(size_t bytes);
+    int use() const;                // cudaSetDevice
+};
+
+struct hnswb200_points {
+    hnswb200_ctx* ctx = nullptr;
+    RecLayout L{};
+    uint64_t n = 0, cap = 0;
+    uint8_t* d_rec = nullptr;
+    std::vector<uint8_t> levels;  // Point.level (points/src/point.rs:8)
+    int reserve(uint64_t want);   // grow device storage, keeps contents
+};
+
+struct hnswb200_graph {
+    hnswb200_ctx* ctx = nullptr;
+    hb::HostGraph h;
+    // device mirror
+    uint32_t* d_adj0 = nullptr;
+    uint64_t rows0_cap = 0, chain0_cap = 0, chain0_used = 0;
+    uint32_t* d_upper_off = nullptr;
+    uint64_t upper_off_cap = 0;
+    uint32_t* d_adju = nullptr;
+    uint64_t rowsu_cap = 0, chainu_cap = 0, chainu_used = 0;
+    std::unordered_map<uint32_t, std::vector<uint32_t>> chains0, chainsu;  // row -> chain rows
+    bool device_valid = false;
+    hb::DevGraph view() const;
+    int upload_full();                                        // (re)build the device mirror
+    int upload_rows(std::vector<uint32_t>& dirty0, std::vector<uint32_t>& dirtyu);  // touched rows only
+    int sync_new_nodes(uint64_t first_new);                   // after HostGraph::add_node calls
+    void free_device();
+};
+
+struct hnswb200_index {
+    hnswb200_ctx* ctx = nullptr;
+    hnswb200_points* points = nullptr;
+    hnswb200_graph* graph = nullptr;
+    hnswb200_params params{};
+};
+
+namespace hb {
+// builder.cu
+int build_insert(hnswb200_ctx* ctx, hnswb200_index* ix, const std::vector<uint32_t>& new_ids, uint32_t batch);
+void draw_levels(uint64_t m, uint64_t n, uint8_t* out);
+// api.cu
+int points_append_f32(hnswb200_ctx* c, hnswb200_points* p, const float* rows, uint64_t n, const uint8_t* levels);
+cudaError_t launch_scatter_rows(uint32_t* dst, uint32_t S, const uint32_t* rows, const uint32_t* data,
+                                uint32_t n, cudaStream_t st);
+}  // namespace hb

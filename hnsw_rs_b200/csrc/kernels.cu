@@ -1,0 +1,588 @@
+// sm_100a kernels of the HNSW query / distance path.
+//   K1 quantise_kernel        <- QuantVec::new                (vectors/src/quant.rs:41-66)
+//   K2 dist_*_kernel          <- distance_unrolled, dist2many, Points::distance/distance2point
+//                                (quant.rs:14-37, vectors/src/lib.rs:17-22, points/src/points.rs:86-101)
+//   K2f dist_full_pairs_kernel<- FullVec::distance             (vectors/src/full.rs:23-29)
+//   K3 search_kernel          <- HNSW::ann_by_vector + search_layer
+//                                (hnsw/src/template.rs:306-335, template/searcher.rs:23-103)
+//   K5 bf_chunk/bf_merge      <- brute_force_nns / sort_by_distance (hnsw/src/helpers/glove.rs:73-109)
+//   K6 topk_merge_kernel      <- (no reference analogue) merge of per-shard top-k lists
+// All of them are HBM-bound byte/gather work; none is GEMM-shaped.
+#include <stdio.h>
+#include <stdlib.h>
+
+#include "kernels.h"
+#include "search.cuh"
+
+namespace hb {
+
+#define HB_DISPATCH_DIM(L, ...)                                                    \
+    do {                                                                           \
+        if ((L).dim == 100) { using Q = RegQuery<12, 4>; __VA_ARGS__; }            \
+        else if ((L).dim == 128) { using Q = RegQuery<16, 0>; __VA_ARGS__; }       \
+        else if ((L).dim == 96) { using Q = RegQuery<12, 0>; __VA_ARGS__; }        \
+        else if ((L).dim == 50) { using Q = RegQuery<6, 2>; __VA_ARGS__; }         \
+        else { using Q = SmemQuery; __VA_ARGS__; }                                 \
+    } while (0)
+
+static inline uint32_t round_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
+
+// ---------------------------------------------------------------------------
+// K1: quantise rows into lane-sliced records
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) quantise_kernel(const float* __restrict__ rows, uint64_t n,
+                                                       RecLayout L, uint8_t* rec, uint8_t* codes,
+                                                       float* mins, float* deltas, uint32_t* nan_flag) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint64_t nwarps = (uint64_t)gridDim.x * (blockDim.x >> 5);
+    for (uint64_t r = warp; r < n; r += nwarps) {
+        const float* v = rows + r * L.dim;
+        float mn, dl;
+        uint8_t* crow = codes ? codes + r * L.dim : nullptr;
+        // pass 1: bounds + flat codes (if requested)
+        bool ok = warp_quantise(v, L.dim, lane, nullptr, crow, mn, dl);
+        if (!ok && lane == 0 && nan_flag) atomicOr(nan_flag, 1u);
+        if (rec) {
+            uint8_t* rp = rec + r * L.stride;
+            for (uint32_t i = lane; i < L.dim; i += 32) {
+                float b = __fadd_rn(__fdiv_rn(__fsub_rn(v[i], mn), dl), 0.5f);
+                float f = fminf(fmaxf(floorf(b), 0.0f), 255.0f);
+                rp[hb_code_offset(L, i)] = (uint8_t)(uint32_t)f;
+            }
+            if (lane == 0) {
+                *reinterpret_cast<float*>(rp + hb_min_offset(L)) = mn;
+                *reinterpret_cast<float*>(rp + hb_delta_offset(L)) = dl;
+            }
+        }
+        if (lane == 0) {
+            if (mins) mins[r] = mn;
+            if (deltas) deltas[r] = dl;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) pack_kernel(const uint8_t* __restrict__ codes,
+                                                   const float* __restrict__ mins,
+                                                   const float* __restrict__ deltas, uint64_t n,
+                                                   RecLayout L, uint8_t* rec) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint64_t nwarps = (uint64_t)gridDim.x * (blockDim.x >> 5);
+    for (uint64_t r = warp; r < n; r += nwarps) {
+        uint8_t* rp = rec + r * L.stride;
+        for (uint32_t i = lane; i < L.dim; i += 32) rp[hb_code_offset(L, i)] = codes[r * L.dim + i];
+        if (lane == 0) {
+            *reinterpret_cast<float*>(rp + hb_min_offset(L)) = mins[r];
+            *reinterpret_cast<float*>(rp + hb_delta_offset(L)) = deltas[r];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) unpack_kernel(const uint8_t* __restrict__ rec, uint64_t n,
+                                                     RecLayout L, uint8_t* codes, float* mins,
+                                                     float* deltas) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint64_t nwarps = (uint64_t)gridDim.x * (blockDim.x >> 5);
+    for (uint64_t r = warp; r < n; r += nwarps) {
+        const uint8_t* rp = rec + r * L.stride;
+        if (codes)
+            for (uint32_t i = lane; i < L.dim; i += 32) codes[r * L.dim + i] = rp[hb_code_offset(L, i)];
+        if (lane == 0) {
+            if (mins) mins[r] = *reinterpret_cast<const float*>(rp + hb_min_offset(L));
+            if (deltas) deltas[r] = *reinterpret_cast<const float*>(rp + hb_delta_offset(L));
+        }
+    }
+}
+
+static inline int grid_for_warps(uint64_t nwarps_needed, int warps_per_block, int cap_blocks = 148 * 16) {
+    uint64_t b = (nwarps_needed + warps_per_block - 1) / warps_per_block;
+    if (b < 1) b = 1;
+    if (b > (uint64_t)cap_blocks) b = cap_blocks;
+    return (int)b;
+}
+
+cudaError_t launch_quantise(const float* rows, uint64_t n, const RecLayout& L, uint8_t* rec,
+                            uint8_t* codes, float* mins, float* deltas, uint32_t* nan_flag,
+                            cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    quantise_kernel<<<grid_for_warps(n, 8), 256, 0, st>>>(rows, n, L, rec, codes, mins, deltas, nan_flag);
+    return cudaGetLastError();
+}
+cudaError_t launch_pack(const uint8_t* codes, const float* mins, const float* deltas, uint64_t n,
+                        const RecLayout& L, uint8_t* rec, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    pack_kernel<<<grid_for_warps(n, 8), 256, 0, st>>>(codes, mins, deltas, n, L, rec);
+    return cudaGetLastError();
+}
+cudaError_t launch_unpack(const uint8_t* rec, uint64_t n, const RecLayout& L, uint8_t* codes,
+                          float* mins, float* deltas, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    unpack_kernel<<<grid_for_warps(n, 8), 256, 0, st>>>(rec, n, L, codes, mins, deltas);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// K2: batched distances
+// ---------------------------------------------------------------------------
+// one f32 query vs ids[n].  distance2point(point, idx) = point.dist2other(points[idx])
+template <class Q>
+__global__ void __launch_bounds__(128) dist_query_many_kernel(const uint8_t* __restrict__ rec, RecLayout L,
+                                                              const float* __restrict__ query,
+                                                              const uint32_t* __restrict__ ids, uint64_t n,
+                                                              float* out, uint32_t* nan_flag) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int gl = lane & 3, gbase = lane & ~3, grp = lane >> 2;
+    const uint32_t qd_cap = (L.dim + 7) / 8 * 8 + 8;
+    float* qd = reinterpret_cast<float*>(smem) + (size_t)wib * qd_cap;
+    float mn, dl;
+    bool ok = warp_quantise(query, L.dim, lane, qd, nullptr, mn, dl);
+    if (!ok && lane == 0 && nan_flag) atomicOr(nan_flag, 1u);
+    __syncwarp();
+    Q q;
+    q.init(L, qd, gl);
+    const uint64_t warp = (uint64_t)blockIdx.x * (blockDim.x >> 5) + wib;
+    const uint64_t nwarps = (uint64_t)gridDim.x * (blockDim.x >> 5);
+    for (uint64_t base = warp * 8; base < n; base += nwarps * 8) {
+        uint64_t i = base + grp;
+        bool act = i < n;
+        uint32_t id = __ldg(ids + (act ? i : base));
+        float d = q.dist(rec + (size_t)id * L.stride, gl, gbase);
+        if (act && gl == 0) out[i] = d;
+    }
+}
+
+cudaError_t launch_dist_query_many(const uint8_t* rec, const RecLayout& L, const float* query,
+                                   const uint32_t* ids, uint64_t n, float* out, uint32_t* nan_flag,
+                                   cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    const uint32_t qd_cap = (L.dim + 7) / 8 * 8 + 8;
+    size_t smem = (size_t)4 * qd_cap * 4;
+    int grid = grid_for_warps((n + 7) / 8, 4, 148 * 8);
+    HB_DISPATCH_DIM(L, {
+        cudaFuncSetAttribute(dist_query_many_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        dist_query_many_kernel<Q><<<grid, 128, smem, st>>>(rec, L, query, ids, n, out, nan_flag);
+    });
+    return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(128) dist_pairs_kernel(const uint8_t* __restrict__ rec, RecLayout L,
+                                                         const uint32_t* __restrict__ a,
+                                                         const uint32_t* __restrict__ b, uint64_t n,
+                                                         float* out) {
+    const int lane = threadIdx.x & 31;
+    const int gl = lane & 3, gbase = lane & ~3, grp = lane >> 2;
+    const uint64_t warp = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint64_t nwarps = (uint64_t)gridDim.x * (blockDim.x >> 5);
+    for (uint64_t base = warp * 8; base < n; base += nwarps * 8) {
+        uint64_t i = base + grp;
+        bool act = i < n;
+        uint64_t j = act ? i : base;
+        float d = rec_rec_dist(L, rec + (size_t)__ldg(a + j) * L.stride, rec + (size_t)__ldg(b + j) * L.stride,
+                               gl, gbase);
+        if (act && gl == 0) out[i] = d;
+    }
+}
+
+cudaError_t launch_dist_pairs(const uint8_t* rec, const RecLayout& L, const uint32_t* a,
+                              const uint32_t* b, uint64_t n, float* out, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    dist_pairs_kernel<<<grid_for_warps((n + 7) / 8, 4, 148 * 8), 128, 0, st>>>(rec, L, a, b, n, out);
+    return cudaGetLastError();
+}
+
+// jobs: out[j] = distance(src[job], ids[j]), j in [off[job], off[job+1]); one warp per job.
+// Used by the build for the prune distances (hnsw/src/template.rs:228-230: x = to_prune, y = n).
+template <class Q>
+__global__ void __launch_bounds__(128) dist_one_to_many_kernel(const uint8_t* __restrict__ rec, RecLayout L,
+                                                               const uint32_t* __restrict__ src,
+                                                               const uint32_t* __restrict__ off,
+                                                               const uint32_t* __restrict__ ids,
+                                                               uint32_t njobs, float* out) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int gl = lane & 3, gbase = lane & ~3, grp = lane >> 2;
+    const uint32_t qd_cap = (L.dim + 7) / 8 * 8 + 8;
+    float* qd = reinterpret_cast<float*>(smem) + (size_t)wib * qd_cap;
+    const uint32_t warp = blockIdx.x * (blockDim.x >> 5) + wib;
+    const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
+    for (uint32_t job = warp; job < njobs; job += nwarps) {
+        __syncwarp();
+        warp_dequant_record(L, rec + (size_t)__ldg(src + job) * L.stride, lane, qd);
+        __syncwarp();
+        Q q;
+        q.init(L, qd, gl);
+        const uint32_t lo = __ldg(off + job), hi = __ldg(off + job + 1);
+        for (uint32_t base = lo; base < hi; base += 8) {
+            uint32_t i = base + grp;
+            bool act = i < hi;
+            uint32_t id = __ldg(ids + (act ? i : base));
+            float d = q.dist(rec + (size_t)id * L.stride, gl, gbase);
+            if (act && gl == 0) out[i] = d;
+        }
+    }
+}
+
+cudaError_t launch_dist_one_to_many(const uint8_t* rec, const RecLayout& L, const uint32_t* src,
+                                    const uint32_t* off, const uint32_t* ids, uint32_t njobs,
+                                    float* out, cudaStream_t st) {
+    if (njobs == 0) return cudaSuccess;
+    const uint32_t qd_cap = (L.dim + 7) / 8 * 8 + 8;
+    size_t smem = (size_t)4 * qd_cap * 4;
+    int grid = grid_for_warps(njobs, 4, 148 * 8);
+    HB_DISPATCH_DIM(L, {
+        cudaFuncSetAttribute(dist_one_to_many_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        dist_one_to_many_kernel<Q><<<grid, 128, smem, st>>>(rec, L, src, off, ids, njobs, out);
+    });
+    return cudaGetLastError();
+}
+
+// K2f: FullVec::distance, one thread per pair, one strictly sequential chain
+__global__ void __launch_bounds__(128) dist_full_pairs_kernel(const float* __restrict__ x,
+                                                              const float* __restrict__ y, uint64_t n,
+                                                              uint32_t dim, float* out) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* a = x + i * dim;
+    const float* b = y + i * dim;
+    float s = 0.0f;
+    for (uint32_t k = 0; k < dim; ++k) {
+        float t = __fsub_rn(a[k], b[k]);
+        s = __fadd_rn(s, __fmul_rn(t, t));
+    }
+    out[i] = __fsqrt_rn(s);
+}
+
+cudaError_t launch_dist_full_pairs(const float* x, const float* y, uint64_t n, uint32_t dim,
+                                   float* out, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    dist_full_pairs_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(x, y, n, dim, out);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// K3: HNSW search, one warp per query, persistent over the batch
+// ---------------------------------------------------------------------------
+struct SearchParams {
+    const uint8_t* rec;
+    RecLayout L;
+    GraphView g;
+    uint32_t n_layers, ep;
+    const float* queries;
+    uint32_t nq, topn, ef, vis_slots;
+    uint32_t ef_cap, qd_cap;
+    uint32_t* out_ids;
+    float* out_dists;
+    uint32_t* out_counts;
+    uint32_t* out_hops;
+    uint32_t* out_evals;
+    uint32_t* out_flags;
+    uint32_t* out_nbrs;
+    uint32_t* work_counter;
+};
+
+constexpr int SEARCH_WPB = 4;
+
+__host__ __device__ inline size_t search_warp_smem(uint32_t ef_cap, uint32_t vis_slots, uint32_t qd_cap) {
+    return (size_t)ef_cap * 8 + (size_t)vis_slots * 4 + 128 + (size_t)qd_cap * 4;
+}
+
+template <class Q>
+__global__ void __launch_bounds__(SEARCH_WPB * 32) search_kernel(SearchParams p) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int gl = lane & 3, gbase = lane & ~3;
+    unsigned char* wsm = smem + (size_t)wib * search_warp_smem(p.ef_cap, p.vis_slots, p.qd_cap);
+    WarpScratch s;
+    s.list = reinterpret_cast<u64*>(wsm);
+    s.vis = reinterpret_cast<uint32_t*>(wsm + (size_t)p.ef_cap * 8);
+    s.newbuf = s.vis + p.vis_slots;
+    s.qd = reinterpret_cast<float*>(s.newbuf + 32);
+    s.vis_slots = p.vis_slots;
+
+    while (true) {
+        uint32_t qi = 0;
+        if (lane == 0) qi = atomicAdd(p.work_counter, 1u);
+        qi = __shfl_sync(HB_FULL, qi, 0);
+        if (qi >= p.nq) break;
+        __syncwarp();
+        // Point::new(vector): the query is quantised exactly like a stored point (template.rs:313)
+        float mn, dl;
+        bool ok = warp_quantise(p.queries + (size_t)qi * p.L.dim, p.L.dim, lane, s.qd, nullptr, mn, dl);
+        __syncwarp();
+        uint32_t* oid = p.out_ids + (size_t)qi * p.topn;
+        float* od = p.out_dists ? p.out_dists + (size_t)qi * p.topn : nullptr;
+        if (!ok) {  // NaN in query: the reference panics; report through flags and an empty result
+            for (uint32_t j = lane; j < p.topn; j += 32) { oid[j] = EMPTY_ID; if (od) od[j] = INFINITY; }
+            if (lane == 0) {
+                if (p.out_counts) p.out_counts[qi] = 0;
+                if (p.out_hops) p.out_hops[qi] = 0;
+                if (p.out_evals) p.out_evals[qi] = 0;
+                if (p.out_flags) p.out_flags[qi] = 1u;
+                if (p.out_nbrs) p.out_nbrs[qi] = 0;
+            }
+            continue;
+        }
+        Q q;
+        q.init(p.L, s.qd, gl);
+        SearchCounters cnt{0u, 1u, 0u, 0u};
+        // selected <- {Dist(ep, distance2point(point, ep))}   (template.rs:316-319)
+        float d0 = q.dist(p.rec + (size_t)p.ep * p.L.stride, gl, gbase);
+        if (lane == 0) s.list[0] = make_key(d0, p.ep);
+        __syncwarp();
+        int n = 1;
+        for (uint32_t layer = p.n_layers - 1; layer >= 1; --layer)  // template.rs:322-324
+            search_layer(q, p.rec, p.L.stride, p.g, layer, s, n, 1, lane, cnt);
+        search_layer(q, p.rec, p.L.stride, p.g, 0u, s, n, (int)p.ef, lane, cnt);  // template.rs:326
+        // get_top_selected(n)   (results.rs:59-61)
+        uint32_t got = min((uint32_t)n, p.topn);
+        for (uint32_t j = lane; j < p.topn; j += 32) {
+            if (j < got) {
+                u64 k = s.list[j];
+                oid[j] = (uint32_t)k;
+                if (od) od[j] = __uint_as_float((uint32_t)(k >> 32));
+            } else {
+                oid[j] = EMPTY_ID;
+                if (od) od[j] = INFINITY;
+            }
+        }
+        if (lane == 0) {
+            if (p.out_counts) p.out_counts[qi] = got;
+            if (p.out_hops) p.out_hops[qi] = cnt.hops;
+            if (p.out_evals) p.out_evals[qi] = cnt.evals;
+            if (p.out_flags) p.out_flags[qi] = cnt.overflow ? 2u : 0u;
+            if (p.out_nbrs) p.out_nbrs[qi] = cnt.nbrs;
+        }
+    }
+}
+
+uint32_t choose_vis_slots(uint32_t ef, uint32_t S0) {
+    // observed: evaluations per query ~ 0.45 * ef * S0 (+ tail); keep the load factor <= ~0.6
+    uint64_t want = (uint64_t)ef * (S0 ? S0 : 32);
+    uint32_t s = 1024;
+    while (s < want && s < (1u << 20)) s <<= 1;
+    return s;
+}
+
+cudaError_t launch_search(const SearchLaunch& a, int num_sms, cudaStream_t st) {
+    if (a.nq == 0) return cudaSuccess;
+    SearchParams p;
+    p.rec = a.rec;
+    p.L = a.L;
+    p.g.adj0 = a.g.adj0; p.g.S0 = a.g.S0; p.g.upper_off = a.g.upper_off; p.g.upper_adj = a.g.upper_adj; p.g.SU = a.g.SU;
+    p.n_layers = a.g.n_layers; p.ep = a.ep;
+    p.queries = a.queries; p.nq = a.nq; p.topn = a.topn; p.ef = a.ef;
+    p.vis_slots = a.vis_slots ? a.vis_slots : choose_vis_slots(a.ef, a.g.S0);
+    if (const char* e = getenv("HNSWB200_VIS_SLOTS")) {  // test knob: force the overflow fallback
+        uint32_t v = (uint32_t)strtoul(e, nullptr, 10);
+        if (v >= 64 && (v & (v - 1)) == 0) p.vis_slots = v;
+    }
+    p.ef_cap = round_up(a.ef, 2);
+    p.qd_cap = round_up(a.L.dim, 8) + 8;
+    p.out_ids = a.out_ids; p.out_dists = a.out_dists; p.out_counts = a.out_counts;
+    p.out_hops = a.out_hops; p.out_evals = a.out_evals; p.out_flags = a.out_flags; p.out_nbrs = a.out_nbrs;
+    p.work_counter = a.work_counter;
+    size_t per_warp = search_warp_smem(p.ef_cap, p.vis_slots, p.qd_cap);
+    // shrink the visited table if one warp would not fit (overflow fallback keeps results exact)
+    while (per_warp * SEARCH_WPB > 200 * 1024 && p.vis_slots > 1024) {
+        p.vis_slots >>= 1;
+        per_warp = search_warp_smem(p.ef_cap, p.vis_slots, p.qd_cap);
+    }
+    size_t smem = per_warp * SEARCH_WPB;
+    if (smem > 227 * 1024) return cudaErrorInvalidValue;
+    cudaError_t e = cudaMemsetAsync(a.work_counter, 0, sizeof(uint32_t), st);
+    if (e != cudaSuccess) return e;
+    HB_DISPATCH_DIM(a.L, {
+        e = cudaFuncSetAttribute(search_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        int occ = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, search_kernel<Q>, SEARCH_WPB * 32, smem);
+        if (e != cudaSuccess) return e;
+        if (occ < 1) occ = 1;
+        uint64_t want = ((uint64_t)a.nq + SEARCH_WPB - 1) / SEARCH_WPB;
+        uint64_t cap = (uint64_t)num_sms * occ;
+        int grid = (int)(want < cap ? want : cap);
+        search_kernel<Q><<<grid, SEARCH_WPB * 32, smem, st>>>(p);
+    });
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// K5: exact brute-force top-k under the quantised metric (CUDA-core version)
+// Base-stationary: a warp keeps one base record dequantised in registers and
+// streams the (L2-resident) query records past it, 8 per round.
+// Orientation as the reference: x = query (self), y = base (glove.rs:99-101).
+// ---------------------------------------------------------------------------
+template <class Q>
+__global__ void __launch_bounds__(128) bf_chunk_kernel(const uint8_t* __restrict__ base_rec, RecLayout L,
+                                                       uint64_t b0, uint64_t b1, uint32_t id_offset,
+                                                       const uint8_t* __restrict__ qrec, uint32_t nq,
+                                                       const uint64_t* __restrict__ tau, uint64_t* buf,
+                                                       uint32_t cap, uint32_t* cnt, uint32_t* overflow) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int gl = lane & 3, gbase = lane & ~3, grp = lane >> 2;
+    const uint32_t qd_cap = (L.dim + 7) / 8 * 8 + 8;
+    float* qd = reinterpret_cast<float*>(smem) + (size_t)wib * qd_cap;
+    const uint64_t warp = (uint64_t)blockIdx.x * (blockDim.x >> 5) + wib;
+    const uint64_t nwarps = (uint64_t)gridDim.x * (blockDim.x >> 5);
+    for (uint64_t b = b0 + warp; b < b1; b += nwarps) {
+        __syncwarp();
+        warp_dequant_record(L, base_rec + b * L.stride, lane, qd);
+        __syncwarp();
+        Q q;
+        q.init(L, qd, gl);
+        const uint32_t gid = (uint32_t)b + id_offset;
+        for (uint32_t r0 = 0; r0 < nq; r0 += 8) {
+            uint32_t qi = r0 + grp;
+            bool act = qi < nq;
+            float d = q.dist(qrec + (size_t)(act ? qi : r0) * L.stride, gl, gbase);
+            if (act && gl == 0) {
+                uint64_t key = make_key(d, gid);
+                if (key < __ldg(tau + qi)) {
+                    uint32_t pos = atomicAdd(cnt + qi, 1u);
+                    if (pos < cap) buf[(size_t)qi * cap + pos] = key;
+                    else atomicOr(overflow, 1u);
+                }
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void block_bitonic_sort(uint64_t* a, uint32_t P) {
+    for (uint32_t k = 2; k <= P; k <<= 1) {
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) {
+                uint32_t ixj = i ^ j;
+                if (ixj > i) {
+                    bool up = (i & k) == 0;
+                    uint64_t x = a[i], y = a[ixj];
+                    if ((x > y) == up) { a[i] = y; a[ixj] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// per query: top-k <- k smallest of (top-k U buffer); tau <- k-th key (or +inf); cnt <- 0
+__global__ void __launch_bounds__(256) bf_merge_kernel(uint64_t* topk, uint32_t k, uint64_t* tau,
+                                                       uint64_t* buf, uint32_t cap, uint32_t* cnt,
+                                                       uint32_t P) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    uint64_t* a = reinterpret_cast<uint64_t*>(smem);
+    const uint32_t qi = blockIdx.x;
+    uint32_t m = min(cnt[qi], cap);
+    for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) {
+        uint64_t v = ~0ull;
+        if (i < k) v = topk[(size_t)qi * k + i];
+        else if (i - k < m) v = buf[(size_t)qi * cap + (i - k)];
+        a[i] = v;
+    }
+    __syncthreads();
+    block_bitonic_sort(a, P);
+    for (uint32_t i = threadIdx.x; i < k; i += blockDim.x) topk[(size_t)qi * k + i] = a[i];
+    if (threadIdx.x == 0) {
+        tau[qi] = a[k - 1];  // ~0 (accept everything) while fewer than k keys are known
+        cnt[qi] = 0;
+    }
+}
+
+__global__ void keys_to_out_kernel(const uint64_t* __restrict__ topk, uint64_t total, uint32_t* ids,
+                                   float* dists) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    uint64_t k = topk[i];
+    if (k == ~0ull) {
+        ids[i] = EMPTY_ID;
+        if (dists) dists[i] = INFINITY;
+    } else {
+        ids[i] = (uint32_t)k;
+        if (dists) dists[i] = __uint_as_float((uint32_t)(k >> 32));
+    }
+}
+
+cudaError_t launch_bf_chunk(const uint8_t* base_rec, const RecLayout& L, uint64_t b0, uint64_t b1,
+                            uint32_t id_offset, const uint8_t* qrec, uint32_t nq, const uint64_t* tau,
+                            uint64_t* buf, uint32_t cap, uint32_t* cnt, uint32_t* overflow,
+                            cudaStream_t st) {
+    if (b1 <= b0 || nq == 0) return cudaSuccess;
+    const uint32_t qd_cap = (L.dim + 7) / 8 * 8 + 8;
+    size_t smem = (size_t)4 * qd_cap * 4;
+    int grid = grid_for_warps(b1 - b0, 4, 148 * 12);
+    HB_DISPATCH_DIM(L, {
+        cudaFuncSetAttribute(bf_chunk_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        bf_chunk_kernel<Q><<<grid, 128, smem, st>>>(base_rec, L, b0, b1, id_offset, qrec, nq, tau, buf, cap, cnt, overflow);
+    });
+    return cudaGetLastError();
+}
+
+static inline uint32_t next_pow2(uint32_t v) {
+    uint32_t p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+cudaError_t launch_bf_merge(uint64_t* topk, uint32_t k, uint64_t* tau, uint64_t* buf, uint32_t cap,
+                            uint32_t* cnt, uint32_t nq, cudaStream_t st) {
+    if (nq == 0) return cudaSuccess;
+    uint32_t P = next_pow2(k + cap);
+    size_t smem = (size_t)P * 8;
+    cudaError_t e = cudaFuncSetAttribute(bf_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    bf_merge_kernel<<<nq, 256, smem, st>>>(topk, k, tau, buf, cap, cnt, P);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_keys_to_out(const uint64_t* topk, uint32_t k, uint32_t nq, uint32_t* ids,
+                               float* dists, cudaStream_t st) {
+    uint64_t total = (uint64_t)k * nq;
+    if (total == 0) return cudaSuccess;
+    keys_to_out_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(topk, total, ids, dists);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// K6: merge G per-shard sorted top-k lists per query under (dist, id) order
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) topk_merge_kernel(const uint32_t* __restrict__ ids,
+                                                         const float* __restrict__ dists, uint32_t G,
+                                                         uint32_t nq, uint32_t k, uint32_t P,
+                                                         uint32_t* out_ids, float* out_dists) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    uint64_t* a = reinterpret_cast<uint64_t*>(smem);
+    const uint32_t qi = blockIdx.x;
+    for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) {
+        uint64_t v = ~0ull;
+        if (i < G * k) {
+            uint32_t g = i / k, j = i % k;
+            size_t src = ((size_t)g * nq + qi) * k + j;
+            uint32_t id = ids[src];
+            if (id != EMPTY_ID) v = make_key(dists[src], id);
+        }
+        a[i] = v;
+    }
+    __syncthreads();
+    block_bitonic_sort(a, P);
+    for (uint32_t i = threadIdx.x; i < k; i += blockDim.x) {
+        uint64_t v = a[i];
+        out_ids[(size_t)qi * k + i] = (v == ~0ull) ? EMPTY_ID : (uint32_t)v;
+        if (out_dists) out_dists[(size_t)qi * k + i] = (v == ~0ull) ? INFINITY : __uint_as_float((uint32_t)(v >> 32));
+    }
+}
+
+cudaError_t launch_topk_merge(const uint32_t* ids, const float* dists, uint32_t G, uint32_t nq,
+                              uint32_t k, uint32_t* out_ids, float* out_dists, cudaStream_t st) {
+    if (nq == 0 || k == 0) return cudaSuccess;
+    uint32_t P = next_pow2(G * k);
+    size_t smem = (size_t)P * 8;
+    if (smem > 200 * 1024) return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    topk_merge_kernel<<<nq, 128, smem, st>>>(ids, dists, G, nq, k, P, out_ids, out_dists);
+    return cudaGetLastError();
+}
+
+}  // namespace hb

@@ -1,0 +1,77 @@
+// Host-callable launchers of the sm_100a kernels (internal C++ interface; the
+// public boundary is include/hnsw_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "layout.h"
+
+namespace hb {
+
+struct DevGraph {
+    const uint32_t* adj0 = nullptr;
+    uint32_t S0 = 0;
+    const uint32_t* upper_off = nullptr;
+    const uint32_t* upper_adj = nullptr;
+    uint32_t SU = 0;
+    uint32_t n_layers = 0;
+};
+
+struct SearchLaunch {
+    const uint8_t* rec;
+    RecLayout L;
+    DevGraph g;
+    uint32_t ep;
+    const float* queries;  // device, nq * dim
+    uint32_t nq, topn, ef;
+    uint32_t vis_slots;    // 0 = choose from ef and the layer-0 row width
+    uint32_t* out_ids;     // nq * topn (EMPTY padded)
+    float* out_dists;      // nq * topn (+inf padded), may be null
+    uint32_t* out_counts;  // nq, may be null
+    uint32_t* out_hops;    // nq, may be null
+    uint32_t* out_evals;   // nq, may be null
+    uint32_t* out_flags;   // nq, may be null (bit0 NaN query, bit1 visited overflow)
+    uint32_t* out_nbrs = nullptr;  // nq, may be null: neighbour ids read
+    uint32_t* work_counter;  // device u32 scratch
+};
+
+// f32 rows -> lane-sliced records (+ optional flat codes/mins/deltas)
+cudaError_t launch_quantise(const float* rows, uint64_t n, const RecLayout& L, uint8_t* rec,
+                            uint8_t* codes, float* mins, float* deltas, uint32_t* nan_flag,
+                            cudaStream_t st);
+cudaError_t launch_pack(const uint8_t* codes, const float* mins, const float* deltas, uint64_t n,
+                        const RecLayout& L, uint8_t* rec, cudaStream_t st);
+cudaError_t launch_unpack(const uint8_t* rec, uint64_t n, const RecLayout& L, uint8_t* codes,
+                          float* mins, float* deltas, cudaStream_t st);
+// distance2point / dist2many: one f32 query (quantised on device) against ids[n]
+cudaError_t launch_dist_query_many(const uint8_t* rec, const RecLayout& L, const float* query,
+                                   const uint32_t* ids, uint64_t n, float* out, uint32_t* nan_flag,
+                                   cudaStream_t st);
+// Points::distance(a[i], b[i])
+cudaError_t launch_dist_pairs(const uint8_t* rec, const RecLayout& L, const uint32_t* a,
+                              const uint32_t* b, uint64_t n, float* out, cudaStream_t st);
+// one stored point against a list of stored points, many such jobs:
+// out[j] = distance(src[job], ids[j]) for j in [off[job], off[job+1])
+cudaError_t launch_dist_one_to_many(const uint8_t* rec, const RecLayout& L, const uint32_t* src,
+                                    const uint32_t* off, const uint32_t* ids, uint32_t njobs,
+                                    float* out, cudaStream_t st);
+// FullVec::distance: strictly sequential f32 sum, x[i*dim..], y[i*dim..]
+cudaError_t launch_dist_full_pairs(const float* x, const float* y, uint64_t n, uint32_t dim,
+                                   float* out, cudaStream_t st);
+cudaError_t launch_search(const SearchLaunch& a, int num_sms, cudaStream_t st);
+uint32_t choose_vis_slots(uint32_t ef, uint32_t S0);
+
+// brute force: one pass over base records [b0, b1) for all queries
+cudaError_t launch_bf_chunk(const uint8_t* base_rec, const RecLayout& L, uint64_t b0, uint64_t b1,
+                            uint32_t id_offset, const uint8_t* qrec, uint32_t nq, const uint64_t* tau,
+                            uint64_t* buf, uint32_t cap, uint32_t* cnt, uint32_t* overflow,
+                            cudaStream_t st);
+cudaError_t launch_bf_merge(uint64_t* topk, uint32_t k, uint64_t* tau, uint64_t* buf, uint32_t cap,
+                            uint32_t* cnt, uint32_t nq, cudaStream_t st);
+cudaError_t launch_keys_to_out(const uint64_t* topk, uint32_t k, uint32_t nq, uint32_t* ids,
+                               float* dists, cudaStream_t st);
+// merge G sorted lists of k (ids/dists [G][nq][k]) into one list of k per query
+cudaError_t launch_topk_merge(const uint32_t* ids, const float* dists, uint32_t G, uint32_t nq,
+                              uint32_t k, uint32_t* out_ids, float* out_dists, cudaStream_t st);
+
+}  // namespace hb

@@ -1,0 +1,73 @@
+// Record layout of a quantised point in HBM ("lane-sliced" record).
+//
+// A QuantVec (vectors/src/quant.rs:6-11: delta, min, codes[dim]) is evaluated by a
+// group of 4 lanes.  The reference accumulates element i into acc[i mod 8] for the
+// first 8*floor(dim/8) elements and every remainder element into acc[0]
+// (quant.rs:14-37).  Lane l of the group owns the accumulator pair
+// (acc[2l], acc[2l+1]) and therefore exactly the bytes code[8k+2l], code[8k+2l+1]
+// for every full chunk k, in increasing k -- the reference's summation order.
+//
+// Memory order is word-major so that the 4 lanes of a group read 64 contiguous
+// bytes with one 16-byte load each:   offset(word j, lane l) = 16 * (4 j + l)
+//   lane slice position p = 2k + {0,1}  ->  word j = p / 16, byte p % 16
+// compact form (tail == 0):
+//   remainder bytes: lane 0, slice positions 2*nch .. 2*nch+rem-1
+//   min   : last 4 bytes of lane 1's last word
+//   delta : last 4 bytes of lane 2's last word
+// tail form (tail == 1), used when the slices have no spare room:
+//   one extra 16-byte word at offset 64*W: [min f32][delta f32][rem bytes][pad]
+// stride = 64*W + 16*tail bytes: 128 B for dim 96/100 (one line per candidate),
+// 144 B for dim 128, 64 B for dim 50.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define HB_HD __host__ __device__ __forceinline__
+#else
+#define HB_HD inline
+#endif
+
+struct RecLayout {
+    uint32_t dim;     // 8*nch + rem
+    uint32_t nch;     // full 8-element chunks
+    uint32_t rem;     // remainder elements (all accumulate into acc[0])
+    uint32_t W;       // 16-byte words per lane slice
+    uint32_t tail;    // 1: trailing [min][delta][rem..] word
+    uint32_t stride;  // bytes per record
+};
+
+HB_HD constexpr uint32_t hb_layout_W(uint32_t nch) {
+    return (2 * nch + 15) / 16 == 0 ? 1u : (2 * nch + 15) / 16;
+}
+HB_HD constexpr uint32_t hb_layout_tail(uint32_t nch, uint32_t rem) {
+    return (16 * hb_layout_W(nch) - 2 * nch >= 4 && 16 * hb_layout_W(nch) - 2 * nch >= rem) ? 0u : 1u;
+}
+
+HB_HD RecLayout hb_make_layout(uint32_t dim) {
+    RecLayout L;
+    L.dim = dim;
+    L.nch = dim / 8;
+    L.rem = dim % 8;
+    L.W = hb_layout_W(L.nch);
+    L.tail = hb_layout_tail(L.nch, L.rem);
+    L.stride = 64 * L.W + 16 * L.tail;
+    return L;
+}
+
+// byte offset of element i of the vector inside its record
+HB_HD uint32_t hb_code_offset(const RecLayout& L, uint32_t i) {
+    if (i < 8 * L.nch) {
+        uint32_t k = i / 8, r = i % 8, l = r / 2, p = 2 * k + (r & 1);
+        return 16 * (4 * (p / 16) + l) + (p % 16);
+    }
+    uint32_t r = i - 8 * L.nch;
+    if (L.tail) return 64 * L.W + 8 + r;
+    uint32_t p = 2 * L.nch + r;
+    return 16 * (4 * (p / 16) + 0) + (p % 16);
+}
+HB_HD uint32_t hb_min_offset(const RecLayout& L) {
+    return L.tail ? 64 * L.W : 16 * (4 * (L.W - 1) + 1) + 12;
+}
+HB_HD uint32_t hb_delta_offset(const RecLayout& L) {
+    return L.tail ? 64 * L.W + 4 : 16 * (4 * (L.W - 1) + 2) + 12;
+}

@@ -1,0 +1,383 @@
+"""GPU parity tests: every call goes through the C ABI (hnsw_rs_b200 -> libhnsw_b200.so) and is
+compared bit for bit with the CPU oracle on the same seeded inputs.  Integer / index results
+must be identical; f32 distances must be bit-identical (the north star allows 1e-5 relative,
+the arithmetic contract gives equality)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+SQRT2 = np.sqrt(np.float32(2.0))
+DIMS = [1, 2, 7, 8, 9, 15, 16, 33, 50, 63, 96, 100, 128, 300]
+
+
+@pytest.fixture(scope="module")
+def H():
+    import hnsw_rs_b200
+    hnsw_rs_b200.Context.default()  # raises if there is no CUDA device: no CPU fallback
+    return hnsw_rs_b200
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def synth(n, dim, ncent, seed, sigma=0.35, normalise=True):
+    rc = np.random.default_rng(1234)
+    cent = rc.standard_normal((ncent, dim), dtype=np.float32)
+    r = np.random.default_rng(seed)
+    x = cent[r.integers(0, ncent, n)] + np.float32(sigma) * r.standard_normal((n, dim), dtype=np.float32)
+    if normalise:
+        x /= np.linalg.norm(x, axis=1, keepdims=True)
+    return x.astype(np.float32)
+
+
+def to_gpu(H, orc):
+    """Import an oracle-built index into the device engine through flat arrays."""
+    codes, mins, deltas, levels = orc.export_points()
+    p = orc.params()
+    prm = H.Params(p["ep"], p["m"], p["mmax"], p["mmax0"], p["ml"], p["ef_cons"], p["dim"])
+    caps = [orc.layer_cap(l) for l in range(orc.nb_layers)]
+    return H.HNSW.from_parts(prm, codes, mins, deltas, levels, orc.export_layers(), caps)
+
+
+def to_oracle(oracle, ix):
+    codes, mins, deltas, levels = ix._points().download()
+    p = ix.params
+    layers = [ix.export_layer(l) for l in range(ix.nb_layers())]
+    return oracle.Index.from_parts(p.m, p.ef_cons, p.dim, p.ep, codes, mins, deltas, levels, layers)
+
+
+def assert_same_graph(a_layers, b_layers):
+    assert len(a_layers) == len(b_layers)
+    for (ai, ao, an), (bi, bo, bn) in zip(a_layers, b_layers):
+        assert np.array_equal(ai, bi)
+        assert np.array_equal(ao, bo)
+        assert np.array_equal(an, bn)
+
+
+# ---- K1 quantiser ------------------------------------------------------------------------
+@pytest.mark.parametrize("dim", DIMS)
+def test_quantise_matches_oracle(H, oracle, dim):
+    rng = np.random.default_rng(dim)
+    rows = rng.normal(size=(257, dim)).astype(np.float32)
+    rows[0] = 0.5                      # constant vector: delta = 0 -> NaN -> code 0
+    rows[1, :] = np.float32(-0.0)      # signed zeros
+    if dim > 1:
+        rows[2, 0], rows[2, 1:] = np.float32(0.0), np.float32(-0.0)
+        rows[3] = np.abs(rows[3]) * np.float32(1e-40)  # denormals
+        rows[4] = rows[4] * np.float32(1e30)
+    codes, mins, deltas = H.quantise_rows(rows)
+    oc, om, od = oracle.quantise_rows(rows)
+    assert np.array_equal(codes, oc)
+    assert np.array_equal(bits(mins), bits(om))
+    assert np.array_equal(bits(deltas), bits(od))
+
+
+def test_quantise_nan_is_an_error(H):
+    rows = np.zeros((4, 10), np.float32)
+    rows[2, 3] = np.nan
+    with pytest.raises(H.HnswB200Error):
+        H.quantise_rows(rows)
+
+
+# ---- K2 distances --------------------------------------------------------------------------
+def test_quantvec_kats(H):  # vectors/src/quant.rs:143-202 through the device
+    q = H.QuantVec.new
+    assert q([0.5]).dist2other(q([0.25])) == np.float32(0.25)
+    assert q([0.75]).dist2other(q([0.25])) == np.float32(0.5)
+    assert q([0.0, 0.0]).dist2other(q([0.0, 1.0])) == np.float32(1.0)
+    assert q([1.0, 0.0]).dist2other(q([0.0, 1.0])) == SQRT2
+    assert q([-1.0, 0.0]).dist2other(q([0.0, 1.0])) == SQRT2
+    assert q([1.0, 0.0]).dist2other(q([0.0, -1.0])) == SQRT2
+    a = q(np.random.default_rng(0).random(128, dtype=np.float32))
+    assert a.dist2other(a) == np.float32(0.0)
+
+
+def test_fullvec_kats(H):  # vectors/src/full.rs:88-147
+    f = H.FullVec.new
+    assert f([0.5]).distance(f([0.25])) == np.float32(0.25)
+    assert f([0.75]).distance(f([0.25])) == np.float32(0.5)
+    assert f([0.0, 0.0]).distance(f([0.0, 1.0])) == np.float32(1.0)
+    assert f([1.0, 0.0]).distance(f([0.0, 1.0])) == SQRT2
+    assert f([-1.0, 0.0]).distance(f([0.0, 1.0])) == SQRT2
+    assert f([1.0, 0.0]).distance(f([0.0, -1.0])) == SQRT2
+
+
+def test_full_and_generic_distance_match_oracle(H, oracle):
+    rng = np.random.default_rng(3)
+    for dim in (1, 5, 128, 300):
+        x = rng.normal(size=(64, dim)).astype(np.float32)
+        y = rng.normal(size=(64, dim)).astype(np.float32)
+        from hnsw_rs_b200.vectors import _dist_full_rows
+        got = _dist_full_rows(x, y)
+        want = np.array([oracle.dist_full(x[i], y[i]) for i in range(64)], np.float32)
+        assert np.array_equal(bits(got), bits(want))
+
+
+def test_dist_err_lt_one_percent(H):  # vectors/tests/full_lvq_tests.rs:3-27
+    rng = np.random.default_rng(7)
+    for _ in range(50):
+        ra, rb = rng.random(128, dtype=np.float32), rng.random(128, dtype=np.float32)
+        full = H.FullVec.new(ra).distance(H.FullVec.new(rb))
+        qa, qb = H.QuantVec.new(ra), H.QuantVec.new(rb)
+        assert abs(full - qa.distance(H.FullVec.new(rb))) / full < 0.01
+        assert abs(full - qa.distance(qb)) / full < 0.01
+        assert abs(full - qa.dist2other(qb)) / full < 0.01
+
+
+@pytest.mark.parametrize("dim", DIMS)
+def test_distances_match_oracle(H, oracle, dim):
+    rng = np.random.default_rng(100 + dim)
+    n = 300
+    rows = (rng.normal(size=(n, dim)) * rng.uniform(0.1, 5.0, size=(n, 1))).astype(np.float32)
+    rows[0] = 1.25  # constant (delta = 0) vector
+    pts = H.SimplePoints.new(rows)
+    codes, mins, deltas, _ = pts.download()
+    oc, om, od = oracle.quantise_rows(rows)
+    assert np.array_equal(codes, oc) and np.array_equal(bits(mins), bits(om)) and np.array_equal(bits(deltas), bits(od))
+    a = rng.integers(0, n, 1000).astype(np.uint32)
+    b = rng.integers(0, n, 1000).astype(np.uint32)
+    got = pts.distances(a, b)
+    want = np.array([oracle.dist_quant((oc[i], om[i], od[i]), (oc[j], om[j], od[j])) for i, j in zip(a, b)], np.float32)
+    assert np.array_equal(bits(got), bits(want))
+    assert np.array_equal(bits(got), bits(pts.distances(b, a)))  # exact symmetry
+    # distance2point / dist2many: the f32 query is quantised first
+    qv = rng.normal(size=dim).astype(np.float32)
+    ids = rng.integers(0, n, 97).astype(np.uint32)
+    got = pts.dist_query_many(qv, ids)
+    qq = oracle.quantise(qv)
+    want = np.array([oracle.dist_quant(qq, (oc[j], om[j], od[j])) for j in ids], np.float32)
+    assert np.array_equal(bits(got), bits(want))
+    assert pts.distance(0, n) is None and pts.distance2point(qv, n) is None
+
+
+# ---- K3 search --------------------------------------------------------------------------------
+def check_search(H, oracle, orc, queries, n, ef):
+    ix = to_gpu(H, orc)
+    ids, dists, counts, st = ix.ann_batch(queries, n, ef, with_stats=True)
+    oids, odists, ocounts, ohops, oevals = orc.search_batch(queries, n, ef)
+    assert np.array_equal(ids, oids)
+    assert np.array_equal(bits(dists), bits(odists))
+    assert np.array_equal(counts, ocounts)
+    assert (st["flags"] == 0).all()
+    assert np.array_equal(st["hops"], ohops)
+    assert np.array_equal(st["evals"], oevals)
+    return ix
+
+
+@pytest.mark.parametrize("ef", [1, 5, 10, 37, 100, 300])
+def test_search_glove_fixture(H, oracle, glove, glove_index, ef):
+    _, queries = glove
+    check_search(H, oracle, glove_index, queries, 10, ef)
+
+
+def test_ann_by_vector_and_recall(H, oracle, glove, glove_index):  # template.rs:518-554
+    store, queries = glove
+    ix = to_gpu(H, glove_index)
+    gt, gd = H.bruteforce_topk(ix._points(), queries, 10)
+    ogt, ogd = glove_index.bruteforce(queries, 10)
+    assert np.array_equal(gt, ogt) and np.array_equal(bits(gd), bits(ogd))
+    hits = 0
+    for i, q in enumerate(queries):
+        ann = ix.ann_by_vector(q, 10, 100)
+        assert ann == glove_index.ann_by_vector(q, 10, 100)
+        hits += len(set(ann) & set(gt[i].tolist()))
+    assert hits / (len(queries) * 10) > 0.99
+    assert len(ix.ann_by_vector(queries[0], 10, 5)) == 5  # ef < n returns ef ids (results.rs:59-61)
+
+
+@pytest.mark.parametrize("dim,n,m,efc", [(100, 6000, 16, 40), (128, 3000, 12, None), (96, 3000, 8, 32), (33, 2000, 5, None)])
+def test_search_synthetic(H, oracle, dim, n, m, efc):
+    base = synth(n, dim, 64, 1, normalise=(dim != 128))
+    queries = synth(200, dim, 64, 2, normalise=(dim != 128))
+    orc = oracle.Index(m, efc, dim).insert_bulk(base)
+    for ef in (1, 10, 64, 150):
+        check_search(H, oracle, orc, queries, 10, ef)
+    check_search(H, oracle, orc, queries, 100, 100)
+    check_search(H, oracle, orc, queries, 3, 50)
+
+
+def test_search_visited_overflow_keeps_results_exact(H, oracle, glove, glove_index, monkeypatch):
+    _, queries = glove
+    ix = to_gpu(H, glove_index)
+    monkeypatch.setenv("HNSWB200_VIS_SLOTS", "64")
+    ids, dists, counts, st = ix.ann_batch(queries, 10, 100, with_stats=True)
+    monkeypatch.delenv("HNSWB200_VIS_SLOTS")
+    oids, odists, ocounts, _, oevals = glove_index.search_batch(queries, 10, 100)
+    assert (st["flags"] & 2).any()
+    assert np.array_equal(ids, oids) and np.array_equal(bits(dists), bits(odists))
+    assert (st["evals"] >= oevals).all()
+
+
+def test_search_errors(H, oracle, glove, glove_index):
+    _, queries = glove
+    ix = to_gpu(H, glove_index)
+    with pytest.raises(H.HnswB200Error):
+        ix.ann_batch(np.zeros((2, 49), np.float32), 10, 10)  # dimension mismatch
+    bad = queries[:3].copy()
+    bad[1, 7] = np.nan
+    with pytest.raises(H.HnswB200Error):
+        ix.ann_batch(bad, 10, 10)  # NaN: the reference panics
+    with pytest.raises(H.HnswB200Error):
+        ix.ann_batch(queries, 10, 0)
+    ids, dists, counts = ix.ann_batch(np.zeros((0, 50), np.float32), 10, 10)
+    assert ids.shape == (0, 10)
+
+
+# ---- K5 brute force / K6 merge -----------------------------------------------------------------
+@pytest.mark.parametrize("dim,n,k", [(100, 20000, 100), (128, 5000, 10), (50, 1000, 1), (33, 3000, 7)])
+def test_bruteforce_matches_oracle(H, oracle, dim, n, k):
+    base = synth(n, dim, 32, 5)
+    base[n // 2] = base[n // 3]  # exact duplicates: ties broken by id
+    queries = synth(64, dim, 32, 6)
+    queries[0] = base[n // 3]
+    orc = oracle.Index(4, None, dim)
+    codes, mins, deltas = oracle.quantise_rows(base)
+    orc2 = oracle.Index.from_parts(4, 8, dim, 0, codes, mins, deltas, np.zeros(n, np.uint8),
+                                   [(np.arange(n, dtype=np.uint32), np.zeros(n + 1, np.uint64), np.zeros(0, np.uint32))])
+    pts = H.SimplePoints.new(base)
+    ids, dists = H.bruteforce_topk(pts, queries, k)
+    oids, odists = orc2.bruteforce(queries, k, threads=8)
+    assert np.array_equal(ids, oids)
+    assert np.array_equal(bits(dists), bits(odists))
+    # base-sharded + merge == unsharded (configs 4 / 5): two shards with global ids
+    half = n // 2
+    s0 = H.SimplePoints.new(base[:half])
+    s1 = H.SimplePoints.new(base[half:])
+    i0, d0 = H.bruteforce_topk(s0, queries, k, 0)
+    i1, d1 = H.bruteforce_topk(s1, queries, k, half)
+    mi, md = H.topk_merge(np.stack([i0, i1]), np.stack([d0, d1]))
+    assert np.array_equal(mi, oids) and np.array_equal(bits(md), bits(odists))
+
+
+def test_bruteforce_adversarial_order(H, oracle):
+    """Base sorted by decreasing distance to the query: every row beats the running threshold, the
+    per-query buffer overflows and the chunk is redone in safe pieces."""
+    dim, n = 16, 12000
+    base = np.zeros((n, dim), np.float32)
+    base[:, 0] = np.linspace(10.0, 1.0, n, dtype=np.float32)
+    base[:, 1] = 1.0
+    q = np.zeros((3, dim), np.float32)
+    q[:, 1] = 1.0
+    q[1, 0] = 0.5
+    codes, mins, deltas = oracle.quantise_rows(base)
+    orc = oracle.Index.from_parts(4, 8, dim, 0, codes, mins, deltas, np.zeros(n, np.uint8),
+                                  [(np.arange(n, dtype=np.uint32), np.zeros(n + 1, np.uint64), np.zeros(0, np.uint32))])
+    ids, dists = H.bruteforce_topk(H.SimplePoints.new(base), q, 10)
+    oids, odists = orc.bruteforce(q, 10)
+    assert np.array_equal(ids, oids) and np.array_equal(bits(dists), bits(odists))
+
+
+# ---- save / load (hnsw/src/template.rs:43-131, 574-611) ---------------------------------------------
+def test_save_load_cross_with_oracle(H, oracle, glove, glove_index, tmp_path):
+    _, queries = glove
+    ix = to_gpu(H, glove_index)
+    ix.save(tmp_path / "gpu")
+    back = oracle.Index.load(tmp_path / "gpu")          # the oracle reads what the engine wrote
+    assert back.params() == glove_index.params()
+    for a, b in zip(back.export_points(), glove_index.export_points()):
+        assert np.array_equal(a, b)
+    assert_same_graph(back.export_layers(), glove_index.export_layers())
+    glove_index.save(tmp_path / "cpu")
+    for name in ("points", "params"):
+        assert (tmp_path / "gpu" / name).read_bytes() == (tmp_path / "cpu" / name).read_bytes()
+    ld = H.HNSW.load(tmp_path / "cpu")                   # the engine reads what the oracle wrote
+    assert ld.len() == 1000 and ld.params.ep == glove_index.ep
+    assert_same_graph([ld.export_layer(l) for l in range(ld.nb_layers())], glove_index.export_layers())
+    a = ld.ann_batch(queries, 10, 100)
+    b = glove_index.search_batch(queries, 10, 100)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(bits(a[1]), bits(b[1]))
+    with pytest.raises(H.HnswB200Error):
+        H.HNSW.load(tmp_path / "missing")
+
+
+# ---- build (hnsw/src/template.rs:177-293, 388-444) ------------------------------------------------
+def test_build_batch1_reproduces_oracle_graph(H, oracle, glove, glove_index):
+    store, queries = glove
+    ix = H.HNSW.new(12, None, 50).insert_bulk(store, batch=1)
+    assert ix.params.ep == glove_index.ep
+    codes, mins, deltas, levels = ix._points().download()
+    oc, om, od, ol = glove_index.export_points()
+    assert np.array_equal(levels, ol) and np.array_equal(codes, oc)
+    assert_same_graph([ix.export_layer(l) for l in range(ix.nb_layers())], glove_index.export_layers())
+
+
+@pytest.mark.parametrize("dim,n,m,efc", [(100, 1500, 16, 60), (128, 800, 6, None), (33, 700, 4, 9)])
+def test_build_batch1_synthetic(H, oracle, dim, n, m, efc):
+    base = synth(n, dim, 16, 11)
+    orc = oracle.Index(m, efc, dim).insert_bulk(base)
+    ix = H.HNSW.new(m, efc, dim).insert_bulk(base, batch=1)
+    assert ix.params.ep == orc.ep
+    assert_same_graph([ix.export_layer(l) for l in range(ix.nb_layers())], orc.export_layers())
+
+
+def test_build_batched_quality_and_search_parity(H, oracle, glove):
+    store, queries = glove
+    ix = H.HNSW.new(12, None, 50).insert_bulk(store)  # default batching
+    assert ix.len() == 1000
+    assert ix.assert_param_compliance()               # template.rs:341-370
+    for l in range(ix.nb_layers()):                   # template.rs:556-571: min degree > 0
+        ids, off, _ = ix.export_layer(l)
+        if len(ids) > 1:
+            assert np.diff(off.astype(np.int64)).min() > 0
+    gt, _ = H.bruteforce_topk(ix._points(), queries, 10)
+    ids, dists, counts, st = ix.ann_batch(queries, 10, 100, with_stats=True)
+    hits = sum(len(set(gt[i].tolist()) & set(ids[i].tolist())) for i in range(len(queries)))
+    assert hits / 1000 > 0.99
+    orc = to_oracle(oracle, ix)                       # oracle search over the device-built graph
+    oids, odists, ocounts, ohops, oevals = orc.search_batch(queries, 10, 100)
+    assert np.array_equal(ids, oids) and np.array_equal(bits(dists), bits(odists))
+    assert np.array_equal(st["hops"], ohops) and np.array_equal(st["evals"], oevals)
+    # graph invariants of graph.rs:305-340: symmetric, no self loops
+    for l in range(ix.nb_layers()):
+        g = ix.get_layer(l)
+        for node in g.iter_nodes():
+            for nb in g.neighbors(node):
+                assert nb != node and node in g.neighbors(nb)
+
+
+def test_build_larger_batched(H, oracle):
+    base = synth(30000, 100, 256, 21)
+    queries = synth(500, 100, 256, 22)
+    ix = H.HNSW.new(16, 100, 100).insert_bulk(base)
+    gt, _ = H.bruteforce_topk(ix._points(), queries, 10)
+    ids, dists, counts, st = ix.ann_batch(queries, 10, 64, with_stats=True)
+    hits = sum(len(set(gt[i].tolist()) & set(ids[i].tolist())) for i in range(len(queries)))
+    assert hits / (10 * len(queries)) > 0.99
+    orc = to_oracle(oracle, ix)
+    oids, odists, _, ohops, oevals = orc.search_batch(queries, 10, 64, threads=8)
+    assert np.array_equal(ids, oids) and np.array_equal(bits(dists), bits(odists))
+    assert np.array_equal(st["hops"], ohops) and np.array_equal(st["evals"], oevals)
+    assert ix.assert_param_compliance()
+
+
+def test_insert_after_build(H, oracle):  # template.rs:479-504
+    rng = np.random.default_rng(5)
+    a = rng.random((100, 10), dtype=np.float32)
+    b = rng.random((100, 10), dtype=np.float32)
+    v = rng.random(10, dtype=np.float32)
+    orc = oracle.Index(12, None, 10).insert_bulk(a)
+    ix = H.HNSW.new(12, None, 10).insert_bulk(a, batch=1)
+    assert orc.insert_vec(v) == ix.insert_vec(v) == 100
+    orc.insert_bulk(b)
+    ix.insert_bulk(b, batch=1)
+    assert ix.len() == 201 and ix.params.ep == orc.ep
+    assert_same_graph([ix.export_layer(l) for l in range(ix.nb_layers())], orc.export_layers())
+    with pytest.raises(H.HnswB200Error):  # can_not_add_different_dim (reference panics)
+        ix.insert_bulk(rng.random((10, 12), dtype=np.float32))
+
+
+def test_extend_loaded_index(H, oracle, tmp_path):
+    """Edge lengths of an imported graph are recomputed on the device before it is extended."""
+    rng = np.random.default_rng(9)
+    a = rng.random((300, 24), dtype=np.float32)
+    b = rng.random((50, 24), dtype=np.float32)
+    orc = oracle.Index(8, None, 24).insert_bulk(a)
+    orc.save(tmp_path / "ix")
+    ix = H.HNSW.load(tmp_path / "ix")
+    ix.insert_bulk(b, batch=1)
+    orc.insert_bulk(b)
+    assert_same_graph([ix.export_layer(l) for l in range(ix.nb_layers())], orc.export_layers())
