@@ -1,0 +1,397 @@
+#!/usr/bin/env python3
+"""bench.py -- queries/sec at recall@10 >= 0.99 on the synthetic GloVe-100-shaped workload
+(BASELINE.json configs[1]: 1,183,514 x 100 unit-norm clustered mixture, 10,000 queries, ef sweep),
+1 B200 per process, one JSON line on rank 0.
+
+    python bench.py --gpus 1 --steps 20 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...      # the CPU restatement of the reference, same config
+
+A step = one pass of HNSW::ann_by_vector over the whole query batch (hnswb200_search_dev).
+value  = queries/s with the queries already resident in HBM (CUDA events, max over ranks).
+e2e    = the same through the host-buffer entry point hnswb200_search (pinned host queries in,
+         ids / distances / counts out), host<->device copies inside the timed region.
+N > 1: the index is replicated, every rank searches its own 10,000 queries (weak scaling), and
+the ids are all-gathered over NCCL inside the timed region so that every rank holds all results.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+EF_SWEEP = [10, 20, 40, 80, 100, 160, 320, 640]
+K = 10
+
+
+def synth(n, dim, ncent, seed, sigma=0.35):
+    """Clustered Gaussian mixture, rows L2-normalised (cosine == L2 on unit vectors)."""
+    rc = np.random.default_rng(1234)
+    cent = rc.standard_normal((ncent, dim), dtype=np.float32)
+    r = np.random.default_rng(seed)
+    x = cent[r.integers(0, ncent, n)]
+    x += np.float32(sigma) * r.standard_normal((n, dim), dtype=np.float32)
+    x /= np.linalg.norm(x, axis=1, keepdims=True)
+    return np.ascontiguousarray(x, np.float32)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=2)
+        except Exception:
+            self.p.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def recall_at_k(ids, gt):
+    hits = 0
+    for i in range(gt.shape[0]):
+        hits += len(set(gt[i].tolist()) & set(ids[i].tolist()))
+    return hits / gt.size
+
+
+def alg_bytes(hops, nbrs, evals, nq, dim, k):
+    """B_q = sum_layers[hops*8 + 4*deg(expanded) + evals*(8+dim)] + 4*dim + 8*k (counted, not modelled)."""
+    return float(hops.astype(np.float64).sum() * 8 + nbrs.astype(np.float64).sum() * 4 +
+                 evals.astype(np.float64).sum() * (8 + dim) + nq * (4 * dim + 8 * k))
+
+
+def oracle_from_index(ix):
+    from oracle import pyoracle as O
+    codes, mins, deltas, levels = ix._points().download()
+    p = ix.params
+    layers = [ix.export_layer(l) for l in range(ix.nb_layers())]
+    return O.Index.from_parts(p.m, p.ef_cons, p.dim, p.ep, codes, mins, deltas, levels, layers)
+
+
+def pick_ef(search_fn, gt, efs):
+    table = []
+    chosen = None
+    for ef in efs:
+        ids = search_fn(ef)
+        r = recall_at_k(ids, gt)
+        table.append((ef, round(r, 5)))
+        if r >= 0.99 and chosen is None:
+            chosen = (ef, r)
+            break
+    if chosen is None:
+        chosen = (efs[-1], table[-1][1])
+    return chosen, table
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n-base", type=int, default=1183514)
+    ap.add_argument("--n-queries", type=int, default=10000)
+    ap.add_argument("--dim", type=int, default=100)
+    ap.add_argument("--m", type=int, default=16)
+    ap.add_argument("--ef-cons", type=int, default=200)
+    ap.add_argument("--ncent", type=int, default=2048)
+    ap.add_argument("--ef", type=int, default=0, help="skip the sweep and use this ef")
+    ap.add_argument("--save-index", default="", help="HNSW::save the built index here (profiling helper)")
+    ap.add_argument("--load-index", default="", help="HNSW::load instead of building (profiling helper)")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the oracle timing (profiling helper)")
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if a.impl == "reference" and rank != 0:
+        return 0  # the CPU arm runs on rank 0 alone
+
+    import torch
+    import hnsw_rs_b200 as H
+    from hnsw_rs_b200 import _ffi
+
+    have_gpu = torch.cuda.is_available()
+    if not have_gpu:
+        raise SystemExit("bench.py needs a CUDA device: hnsw_rs_b200 has no CPU fallback "
+                         "(the reference arm also builds its index with the device builder)")
+    torch.cuda.set_device(local_rank)
+    if world > 1 and a.impl == "b200":
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = H.Context(local_rank)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+
+    workload = (f"C2 synthetic GloVe-100 shape: {a.n_base}x{a.dim} unit-norm clustered mixture ({a.ncent} centres, "
+                f"sigma 0.35, seed 1), {a.n_queries} queries/GPU (seed 2+rank), k={K}, quantised-L2 (== cosine rank)")
+    queries = synth(a.n_queries, a.dim, a.ncent, 2 + rank)
+    nq, dim = queries.shape
+
+    t0 = time.time()
+    if a.load_index:
+        ix = H.HNSW.load(a.load_index, ctx=ctx)
+    else:
+        base = synth(a.n_base, a.dim, a.ncent, 1)
+        t0 = time.time()
+        ix = H.HNSW.new(a.m, a.ef_cons, a.dim, ctx=ctx).insert_bulk(base)
+        del base
+    build_s = time.time() - t0
+    if a.save_index and rank == 0:
+        ix.save(a.save_index)
+
+    # exact ground truth under the quantised metric on the device (K5)
+    t0 = time.time()
+    gt, _ = H.bruteforce_topk(ix._points(), queries, K, ctx=ctx)
+    gt_s = time.time() - t0
+
+    dq = torch.from_numpy(queries).cuda()
+    d_ids = torch.empty((nq, K), dtype=torch.int32, device="cuda")
+    d_d = torch.empty((nq, K), dtype=torch.float32, device="cuda")
+    d_cnt = torch.empty(nq, dtype=torch.int32, device="cuda")
+    d_h = torch.empty(nq, dtype=torch.int32, device="cuda")
+    d_e = torch.empty(nq, dtype=torch.int32, device="cuda")
+    d_f = torch.empty(nq, dtype=torch.int32, device="cuda")
+    d_nb = torch.empty(nq, dtype=torch.int32, device="cuda")
+    lib = _ffi.lib()
+
+    def search_dev(ef):
+        _ffi.check(lib.hnswb200_search_dev(ctx.h, ix.h, dq.data_ptr(), nq, K, ef, d_ids.data_ptr(), d_d.data_ptr(),
+                                           d_cnt.data_ptr(), d_h.data_ptr(), d_e.data_ptr(), d_f.data_ptr(),
+                                           d_nb.data_ptr()))
+
+    def search_ids(ef):
+        search_dev(ef)
+        torch.cuda.synchronize()
+        return d_ids.cpu().numpy().astype(np.uint32)
+
+    if a.ef:
+        ef, rec = a.ef, recall_at_k(search_ids(a.ef), gt)
+        sweep = [(ef, round(rec, 5))]
+    else:
+        (ef, rec), sweep = pick_ef(search_ids, gt, EF_SWEEP)
+    if world > 1 and a.impl == "b200":
+        # every rank must run the same ef: take the largest any rank needs
+        t = torch.tensor([ef], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ef = int(t.item())
+        rec = recall_at_k(search_ids(ef), gt)
+
+    cfg = {"workload": workload, "index": "HNSW M=%d ef_cons=%d, built on the device (batched inserts), replicated per GPU"
+           % (a.m, a.ef_cons), "ef": ef, "recall_at_10": round(rec, 5), "ef_sweep": sweep,
+           "build_seconds": round(build_s, 2), "ground_truth_seconds": round(gt_s, 2),
+           "l2": "index (records + adjacency) is %.0f MB > 126 MB L2; no flush between steps"
+                 % ((ix.len() * (128 + 4 * 2 * a.m)) / 1e6)}
+
+    if a.impl == "reference":
+        return run_reference(a, ix, queries, gt, ef, rec, cfg)
+
+    # ---------------- device-resident throughput (value) ----------------
+    for _ in range(a.warmup):
+        search_dev(ef)
+    torch.cuda.synchronize()
+    if world > 1:
+        gathered = torch.empty((world, nq, K), dtype=torch.int32, device="cuda")
+        dist.all_gather_into_tensor(gathered, d_ids)
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    e0.record()
+    for s in range(a.steps):
+        k_ev[s][0].record()
+        search_dev(ef)
+        k_ev[s][1].record()
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, d_ids)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    total_ms = e0.elapsed_time(e1)
+    kern_ms = float(np.mean([x.elapsed_time(y) for x, y in k_ev]))
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    value = world * nq * a.steps / (total_ms / 1e3)
+
+    hops = d_h.cpu().numpy().astype(np.uint32)
+    evals = d_e.cpu().numpy().astype(np.uint32)
+    nbrs = d_nb.cpu().numpy().astype(np.uint32)
+    flags = d_f.cpu().numpy()
+    ab = alg_bytes(hops, nbrs, evals, nq, dim, K)
+
+    # ---------------- end to end through the host-buffer entry point ----------------
+    hq = torch.from_numpy(queries).pin_memory()
+    h_ids = torch.empty((nq, K), dtype=torch.int32).pin_memory()
+    h_d = torch.empty((nq, K), dtype=torch.float32).pin_memory()
+    h_c = torch.empty(nq, dtype=torch.int32).pin_memory()
+
+    def search_host():
+        _ffi.check(lib.hnswb200_search(ctx.h, ix.h, C.cast(hq.data_ptr(), _ffi.f32p), nq, dim, K, ef,
+                                       C.cast(h_ids.data_ptr(), _ffi.u32p), C.cast(h_d.data_ptr(), _ffi.f32p),
+                                       C.cast(h_c.data_ptr(), _ffi.u32p), None))
+
+    for _ in range(a.warmup):
+        search_host()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        search_host()  # synchronous: returns when the results are in host memory
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    assert np.array_equal(h_ids.numpy(), d_ids.cpu().numpy()), "host and device entry points disagree"
+    e2e = {"value": world * nq * a.steps / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": int(nq * dim * 4),
+           "d2h_bytes_per_step": int(nq * K * 8 + nq * 4 + nq * 4)}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = ab / (kern_ms / 1e3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "search_kernel_traffic.json"))).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": "hb::search_kernel<RegQuery<12,4>>", "achieved": round(achieved, 1),
+                "peak": peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
+                "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
+                "algorithmic_bytes_per_launch": ab, "kernel_ms": round(kern_ms, 4),
+                "per_query": {"hops": float(hops.mean()), "evals": float(evals.mean()), "nbr_ids": float(nbrs.mean()),
+                              "bytes": ab / nq}, "visited_overflow_queries": int((flags & 2).sum())}
+
+    # ---------------- CPU baseline: the oracle (port of the reference) on this box's cores ----------------
+    if a.no_cpu_baseline:
+        line = {"metric": "queries/sec at recall@10>=0.99", "value": value, "unit": "queries/s", "n_gpus": world,
+                "steps": a.steps, "warmup": a.warmup, "ms_per_step": total_ms / a.steps, "config": cfg, "e2e": e2e,
+                "roofline": roofline, "clocks": clocks, "note": "profiling helper run, no cpu_baseline"}
+        print(json.dumps(line), flush=True)
+        return 0
+    orc = oracle_from_index(ix)
+    cores = os.cpu_count() or 1
+    sample = queries
+    orc.search_batch(sample[:256], K, ef, threads=cores)  # warm-up
+    best = None
+    for _ in range(3):
+        t0 = time.perf_counter()
+        oids, _, _, oh, oe = orc.search_batch(sample, K, ef, threads=cores)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    parity = bool(np.array_equal(oids, d_ids.cpu().numpy().astype(np.uint32)) and np.array_equal(oh, hops)
+                  and np.array_equal(oe, evals))
+    n1 = min(2000, nq)
+    t0 = time.perf_counter()
+    orc.search_batch(sample[:n1], K, ef, threads=1)
+    dt1 = time.perf_counter() - t0
+    cpu = {"value": len(sample) / best, "unit": "queries/s", "cores": cores, "kind": "port",
+           "sample": f"all {len(sample)} queries of the step at ef={ef}, best of 3 passes, {cores} threads over a shared "
+                     f"read-only index (the graph the device built)",
+           "single_thread_qps": n1 / dt1, "ids_and_counters_identical_to_gpu": parity}
+
+    line = {"metric": "queries/sec at recall@10>=0.99", "value": value, "unit": "queries/s", "n_gpus": world,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": total_ms / a.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+            "e2e": e2e, "gpu_launches": a.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def run_reference(a, ix, queries, gt, ef, rec, cfg):
+    """The reference's own CPU implementation of the path (the oracle port: no Rust toolchain here),
+    all host threads, same index / queries / ef.  One step = all queries of the batch."""
+    orc = oracle_from_index(ix)
+    cores = os.cpu_count() or 1
+    nq = queries.shape[0]
+    for _ in range(a.warmup):
+        orc.search_batch(queries, K, ef, threads=cores)
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        ids, _, _, _, _ = orc.search_batch(queries, K, ef, threads=cores)
+    dt = time.perf_counter() - t0
+    value = nq * a.steps / dt
+    cfg = dict(cfg)
+    cfg["recall_at_10_cpu"] = round(recall_at_k(ids, gt), 5)
+    cfg["index_built_by"] = "device builder (setup, untimed); the oracle searches that graph"
+    line = {"impl": "reference", "metric": "queries/sec at recall@10>=0.99", "value": value, "unit": "queries/s",
+            "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": cfg,
+            "cpu_baseline": {"value": value, "unit": "queries/s", "cores": cores, "kind": "port",
+                             "sample": f"all {nq} queries per step at ef={ef}, {cores} threads"},
+            "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -15,9 +15,12 @@
 // nb_threads > 1 mode, where concurrently inserted points do not see each other's
 // edges either (template.rs:401-440) -- but deterministic.
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <vector>
 
 #include "engine.h"
@@ -544,7 +547,13 @@ int build_insert(hnswb200_ctx* c, hnswb200_index* ix, const std::vector<uint32_t
     uint64_t linked = h.n_points() - new_ids.size();
     size_t pos = 0;
     std::vector<LayerSel> res;
+    const bool prof = getenv("HNSWB200_BUILD_PROFILE") != nullptr;
+    double t_kernel = 0, t_commit = 0, t_upload = 0;
+    uint64_t n_batches = 0;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     while (pos < order.size()) {
+        double t0 = now();
+        ++n_batches;
         // ramp: a batch never exceeds a quarter of what is already linked, so early
         // points (which shape the upper layers) are inserted (almost) one by one
         uint64_t lim = batch == 1 ? 1 : std::max<uint64_t>(1, linked / 4);
@@ -562,6 +571,7 @@ int build_insert(hnswb200_ctx* c, hnswb200_index* ix, const std::vector<uint32_t
         HB_CUDA(cudaMemcpyAsync(o_d.data(), d_od.p, (size_t)nb * nl * m * 4, cudaMemcpyDeviceToHost, c->stream));
         HB_CUDA(cudaMemcpyAsync(o_cnt.data(), d_ocnt.p, (size_t)nb * nl * 4, cudaMemcpyDeviceToHost, c->stream));
         HB_CUDA(cudaStreamSynchronize(c->stream));
+        double t1 = now();
         for (uint32_t j = 0; j < nb; ++j) {
             uint32_t pid = order[pos + j];
             res.clear();
@@ -579,11 +589,17 @@ int build_insert(hnswb200_ctx* c, hnswb200_index* ix, const std::vector<uint32_t
             rc = commit_point(h, pid, res, d0, du);
             if (rc) return rc;
         }
+        double t2 = now();
         rc = G->upload_rows(d0, du);
         if (rc) return rc;
         pos += nb;
         linked += nb;
+        double t3 = now();
+        t_kernel += t1 - t0; t_commit += t2 - t1; t_upload += t3 - t2;
     }
+    if (prof)
+        fprintf(stderr, "[hnswb200 build] points=%zu batches=%llu kernel+copy=%.3fs commit=%.3fs upload=%.3fs smem/block=%zu grid_cap=%d\n",
+                order.size(), (unsigned long long)n_batches, t_kernel, t_commit, t_upload, smem, grid_cap);
     return 0;
 }
 
