@@ -357,6 +357,13 @@ void hnswb200_graph::free_device() {
     if (d_adju) cudaFree(d_adju);
     d_adj0 = d_upper_off = d_adju = nullptr;
     device_valid = false;
+    if (h_stage_rows) cudaFreeHost(h_stage_rows);
+    if (h_stage_data) cudaFreeHost(h_stage_data);
+    if (d_stage_rows) cudaFree(d_stage_rows);
+    if (d_stage_data) cudaFree(d_stage_data);
+    h_stage_rows = h_stage_data = d_stage_rows = d_stage_data = nullptr;
+    stage_cap = 0;
+    stage_S = 0;
 }
 
 namespace {
@@ -483,29 +490,69 @@ int hnswb200_graph::upload_rows(std::vector<uint32_t>& dirty0, std::vector<uint3
     for (int which = 0; which < 2; ++which) {
         std::vector<uint32_t>& dirty = which ? dirtyu : dirty0;
         if (dirty.empty()) continue;
-        std::sort(dirty.begin(), dirty.end());
-        dirty.erase(std::unique(dirty.begin(), dirty.end()), dirty.end());
         const hb::AdjStore& s = which ? h.au : h.a0;
-        std::vector<uint32_t> rows, data;
-        ListSink sink(rows, data, s.S);
-        bool ok = true;
+        const uint32_t S = s.S;
+        // de-duplicate with a mark array (the list holds every touched row, often many times)
+        std::vector<uint8_t>& mark = which ? marku : mark0;
+        if (mark.size() < s.rows()) mark.resize(s.rows(), 0);
+        size_t uniq = 0;
+        for (uint32_t r : dirty)
+            if (!mark[r]) { mark[r] = 1; dirty[uniq++] = r; }
+        dirty.resize(uniq);
+        for (uint32_t r : dirty) mark[r] = 0;
+        // stage: rows whose degree fits are already in device form on the host
+        size_t need = uniq + 64;
+        const uint32_t Smax = std::max(h.a0.S, h.au.S);
+        if (stage_cap < need || stage_S < Smax) {
+            if (h_stage_rows) cudaFreeHost(h_stage_rows);
+            if (h_stage_data) cudaFreeHost(h_stage_data);
+            if (d_stage_rows) cudaFree(d_stage_rows);
+            if (d_stage_data) cudaFree(d_stage_data);
+            h_stage_rows = h_stage_data = d_stage_rows = d_stage_data = nullptr;
+            stage_cap = std::max(stage_cap, need + need / 2);
+            stage_S = Smax;
+            HB_CUDA(cudaHostAlloc((void**)&h_stage_rows, stage_cap * 4, cudaHostAllocDefault));
+            HB_CUDA(cudaHostAlloc((void**)&h_stage_data, stage_cap * (size_t)stage_S * 4, cudaHostAllocDefault));
+            HB_CUDA(cudaMalloc((void**)&d_stage_rows, stage_cap * 4));
+            HB_CUDA(cudaMalloc((void**)&d_stage_data, stage_cap * (size_t)stage_S * 4));
+        }
+        size_t cnt = 0;
+        std::vector<uint32_t> big;  // rows that need continuation rows: rare
         for (uint32_t r : dirty) {
-            ok = which ? materialise_row(s, r, rowsu_cap, chainu_cap, chainu_used, chainsu, sink)
-                       : materialise_row(s, r, rows0_cap, chain0_cap, chain0_used, chains0, sink);
-            if (!ok) break;
+            if (s.deg[r] <= S) {
+                h_stage_rows[cnt] = r;
+                memcpy(h_stage_data + cnt * S, &s.data[(size_t)r * S], (size_t)S * 4);
+                ++cnt;
+            } else {
+                big.push_back(r);
+            }
         }
-        if (!ok) {  // out of continuation rows: rebuild with more head-room
-            dirty0.clear();
-            dirtyu.clear();
-            return upload_full();
+        if (!big.empty()) {
+            std::vector<uint32_t> rows, data;
+            ListSink sink(rows, data, S);
+            for (uint32_t r : big) {
+                bool ok = which ? materialise_row(s, r, rowsu_cap, chainu_cap, chainu_used, chainsu, sink)
+                                : materialise_row(s, r, rows0_cap, chain0_cap, chain0_used, chains0, sink);
+                if (!ok) {  // out of continuation rows: rebuild with more head-room
+                    dirty0.clear();
+                    dirtyu.clear();
+                    return upload_full();
+                }
+            }
+            if (cnt + rows.size() > stage_cap) {  // cannot happen with the +64 slack unless many chains
+                dirty0.clear();
+                dirtyu.clear();
+                return upload_full();
+            }
+            for (size_t i = 0; i < rows.size(); ++i) {
+                h_stage_rows[cnt] = rows[i];
+                memcpy(h_stage_data + cnt * S, &data[i * S], (size_t)S * 4);
+                ++cnt;
+            }
         }
-        hb::DevBuf<uint32_t> d_rows, d_data;
-        HB_CUDA(d_rows.alloc(rows.size()));
-        HB_CUDA(d_data.alloc(data.size()));
-        HB_CUDA(cudaMemcpyAsync(d_rows.p, rows.data(), rows.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
-        HB_CUDA(cudaMemcpyAsync(d_data.p, data.data(), data.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
-        HB_CUDA(hb::launch_scatter_rows(which ? d_adju : d_adj0, s.S, d_rows.p, d_data.p, (uint32_t)rows.size(),
-                                        ctx->stream));
+        HB_CUDA(cudaMemcpyAsync(d_stage_rows, h_stage_rows, cnt * 4, cudaMemcpyHostToDevice, ctx->stream));
+        HB_CUDA(cudaMemcpyAsync(d_stage_data, h_stage_data, cnt * (size_t)S * 4, cudaMemcpyHostToDevice, ctx->stream));
+        HB_CUDA(hb::launch_scatter_rows(which ? d_adju : d_adj0, S, d_stage_rows, d_stage_data, (uint32_t)cnt, ctx->stream));
         HB_CUDA(cudaStreamSynchronize(ctx->stream));
         dirty.clear();
     }
@@ -663,6 +710,7 @@ int hnswb200_search_dev(hnswb200_ctx* c, const hnswb200_index* ix, const float* 
     a.L = ix->points->L;
     a.g = ix->graph->view();
     a.ep = ix->params.ep;
+    a.n_points = ix->points->n;
     a.queries = d_queries;
     a.nq = (uint32_t)nq;
     a.topn = n;

@@ -378,8 +378,16 @@ struct LayerSel {
     std::vector<float> dists;
 };
 
+struct CommitScratch {
+    struct Prune { uint32_t layer, node, kept_off, kept_n, drop_off, drop_n; };
+    std::vector<Prune> prunes;
+    std::vector<uint32_t> kept_ids, drop_ids, lost;
+    std::vector<float> kept_w;
+    std::vector<std::pair<u64, uint32_t>> keyed;
+};
+
 static int commit_point(HostGraph& h, uint32_t pid, const std::vector<LayerSel>& res,
-                        std::vector<uint32_t>& dirty0, std::vector<uint32_t>& dirtyu) {
+                        std::vector<uint32_t>& dirty0, std::vector<uint32_t>& dirtyu, CommitScratch& cs) {
     // make_connections: every layer first (ascending layer, ascending Dist)
     for (const LayerSel& ls : res) {
         std::vector<uint32_t>* dirty = ls.layer == 0 ? &dirty0 : &dirtyu;
@@ -390,9 +398,10 @@ static int commit_point(HostGraph& h, uint32_t pid, const std::vector<LayerSel>&
     }
     // prune_connections: for every new neighbour x above the layer cap keep the cap nearest
     // (select_simple, template.rs:614-621).  All results are computed before any is applied.
-    struct Prune { uint32_t layer, node; std::vector<uint32_t> ids; std::vector<float> w; };
-    std::vector<Prune> prunes;
-    std::vector<std::pair<u64, uint32_t>> keyed;
+    cs.prunes.clear();
+    cs.kept_ids.clear();
+    cs.kept_w.clear();
+    cs.drop_ids.clear();
     for (const LayerSel& ls : res) {
         const AdjStore& s = h.store(ls.layer);
         const uint32_t cap = h.cap(ls.layer);
@@ -400,35 +409,61 @@ static int commit_point(HostGraph& h, uint32_t pid, const std::vector<LayerSel>&
             uint32_t row = h.row(x, ls.layer);
             uint32_t d = s.deg[row];
             if (!(d > cap)) continue;
-            bool seen = false;  // prune_results is a map: one entry per (layer, node)
-            for (const Prune& pr : prunes) if (pr.layer == ls.layer && pr.node == x) { seen = true; break; }
-            if (seen) continue;
-            keyed.clear();
+            // (prune_results is a map keyed by node; a node occurs once in one point's selection)
+            cs.keyed.clear();
             for (uint32_t i = 0; i < d; ++i) {
                 float w = s.getw(row, i);
                 uint32_t bits;
                 memcpy(&bits, &w, 4);
-                keyed.push_back({((u64)bits << 32) | s.get(row, i), i});
+                cs.keyed.push_back({((u64)bits << 32) | s.get(row, i), i});
             }
-            std::sort(keyed.begin(), keyed.end());
-            Prune pr;
+            // keep the `cap` smallest (dist, id) keys; almost always d == cap + 1
+            std::nth_element(cs.keyed.begin(), cs.keyed.begin() + cap, cs.keyed.end());
+            CommitScratch::Prune pr;
             pr.layer = ls.layer;
             pr.node = x;
-            for (uint32_t i = 0; i < cap && i < keyed.size(); ++i) {
-                pr.ids.push_back((uint32_t)keyed[i].first);
-                pr.w.push_back(s.getw(row, keyed[i].second));
+            pr.kept_off = (uint32_t)cs.kept_ids.size();
+            pr.kept_n = cap;
+            pr.drop_off = (uint32_t)cs.drop_ids.size();
+            pr.drop_n = d - cap;
+            for (uint32_t i = 0; i < d; ++i) {
+                if (i < cap) {
+                    cs.kept_ids.push_back((uint32_t)cs.keyed[i].first);
+                    cs.kept_w.push_back(s.getw(row, cs.keyed[i].second));
+                } else {
+                    cs.drop_ids.push_back((uint32_t)cs.keyed[i].first);
+                }
             }
-            prunes.push_back(std::move(pr));
+            cs.prunes.push_back(pr);
         }
     }
     // make_pruned_connections: ascending layer, ascending node id (oracle convention for the
-    // reference's hash-map iteration order)
-    std::sort(prunes.begin(), prunes.end(), [](const Prune& a, const Prune& b) {
+    // reference's hash-map iteration order).  replace_neighbors(x, kept) = isolate_node(x) +
+    // add_neighbors(x, kept) (graph.rs:85-94,128-148): members of `kept` are removed and re-added
+    // (no net change), the others lose the edge unless their degree is 1.  A kept edge has to be
+    // re-created only if an earlier replacement of this same point cut it, i.e. x lost an edge.
+    std::sort(cs.prunes.begin(), cs.prunes.end(), [](const CommitScratch::Prune& a, const CommitScratch::Prune& b) {
         return a.layer != b.layer ? a.layer < b.layer : a.node < b.node;
     });
-    for (const Prune& pr : prunes) {
-        int r = h.replace_neighbors(pr.layer, pr.node, pr.ids, pr.w, pr.layer == 0 ? &dirty0 : &dirtyu);
-        if (r) { set_error("make_pruned_connections: replace_neighbors failed"); return HNSWB200_ESTATE; }
+    cs.lost.clear();
+    uint32_t lost_layer = 0xFFFFFFFFu;
+    for (const CommitScratch::Prune& pr : cs.prunes) {
+        std::vector<uint32_t>* dirty = pr.layer == 0 ? &dirty0 : &dirtyu;
+        if (pr.layer != lost_layer) { cs.lost.clear(); lost_layer = pr.layer; }
+        const bool x_lost = std::find(cs.lost.begin(), cs.lost.end(), pr.node) != cs.lost.end();
+        for (uint32_t i = 0; i < pr.drop_n; ++i) {
+            uint32_t nb = cs.drop_ids[pr.drop_off + i];
+            if (h.store(pr.layer).find(h.row(pr.node, pr.layer), nb) < 0) continue;  // already cut earlier
+            if (h.degree(nb, pr.layer) == 1) continue;
+            h.remove_edge(pr.layer, pr.node, nb, dirty);
+            cs.lost.push_back(nb);
+        }
+        if (x_lost) {
+            for (uint32_t i = 0; i < pr.kept_n; ++i) {
+                int r = h.add_edge(pr.layer, pr.node, cs.kept_ids[pr.kept_off + i], cs.kept_w[pr.kept_off + i], dirty);
+                if (r) { set_error("make_pruned_connections: replace_neighbors failed"); return HNSWB200_ESTATE; }
+            }
+        }
     }
     return 0;
 }
@@ -547,6 +582,7 @@ int build_insert(hnswb200_ctx* c, hnswb200_index* ix, const std::vector<uint32_t
     uint64_t linked = h.n_points() - new_ids.size();
     size_t pos = 0;
     std::vector<LayerSel> res;
+    CommitScratch cs;
     const bool prof = getenv("HNSWB200_BUILD_PROFILE") != nullptr;
     double t_kernel = 0, t_commit = 0, t_upload = 0;
     uint64_t n_batches = 0;
@@ -586,7 +622,7 @@ int build_insert(hnswb200_ctx* c, hnswb200_index* ix, const std::vector<uint32_t
                 ls.dists.assign(od, od + cnt);
                 res.push_back(std::move(ls));
             }
-            rc = commit_point(h, pid, res, d0, du);
+            rc = commit_point(h, pid, res, d0, du, cs);
             if (rc) return rc;
         }
         double t2 = now();

@@ -62,6 +62,11 @@ struct hnswb200_graph {
     uint64_t rowsu_cap = 0, chainu_cap = 0, chainu_used = 0;
     std::unordered_map<uint32_t, std::vector<uint32_t>> chains0, chainsu;  // row -> chain rows
     bool device_valid = false;
+    // staging for incremental row uploads (pinned host + device, grow-only)
+    uint32_t *h_stage_rows = nullptr, *h_stage_data = nullptr, *d_stage_rows = nullptr, *d_stage_data = nullptr;
+    size_t stage_cap = 0;
+    uint32_t stage_S = 0;
+    std::vector<uint8_t> mark0, marku;
     hb::DevGraph view() const;
     int upload_full();                                        // (re)build the device mirror
     int upload_rows(std::vector<uint32_t>& dirty0, std::vector<uint32_t>& dirtyu);  // touched rows only

@@ -13,6 +13,7 @@
 
 #include "kernels.h"
 #include "search.cuh"
+#include "search_reg.cuh"
 
 namespace hb {
 
@@ -273,6 +274,7 @@ struct SearchParams {
     const float* queries;
     uint32_t nq, topn, ef, vis_slots;
     uint32_t ef_cap, qd_cap;
+    uint32_t tbits, bbits;  // fast path: 16-bit visited table geometry
     uint32_t* out_ids;
     float* out_dists;
     uint32_t* out_counts;
@@ -358,6 +360,97 @@ __global__ void __launch_bounds__(SEARCH_WPB * 32) search_kernel(SearchParams p)
     }
 }
 
+
+// Fast path: register-resident list (KPL keys per lane), 16-bit visited table.
+__host__ __device__ inline size_t fast_warp_smem(uint32_t tbits, uint32_t qd_cap) {
+    return ((size_t)2 << tbits) + 128 + (size_t)qd_cap * 4;
+}
+
+template <class Q, int KPL>
+__global__ void __launch_bounds__(SEARCH_WPB * 32) search_fast_kernel(SearchParams p) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int gl = lane & 3, gbase = lane & ~3;
+    unsigned char* wsm = smem + (size_t)wib * fast_warp_smem(p.tbits, p.qd_cap);
+    WarpScratch16 s;
+    s.vis.words = reinterpret_cast<uint32_t*>(wsm);
+    s.vis.tbits = p.tbits;
+    s.vis.bbits = p.bbits;
+    s.vis.bmask = (p.bbits >= 32) ? 0xFFFFFFFFu : ((1u << p.bbits) - 1u);
+    s.newbuf = reinterpret_cast<uint32_t*>(wsm + ((size_t)2 << p.tbits));
+    s.qd = reinterpret_cast<float*>(s.newbuf + 32);
+
+    while (true) {
+        uint32_t qi = 0;
+        if (lane == 0) qi = atomicAdd(p.work_counter, 1u);
+        qi = __shfl_sync(HB_FULL, qi, 0);
+        if (qi >= p.nq) break;
+        __syncwarp();
+        float mn, dl;
+        bool ok = warp_quantise(p.queries + (size_t)qi * p.L.dim, p.L.dim, lane, s.qd, nullptr, mn, dl);
+        __syncwarp();
+        uint32_t* oid = p.out_ids + (size_t)qi * p.topn;
+        float* od = p.out_dists ? p.out_dists + (size_t)qi * p.topn : nullptr;
+        if (!ok) {
+            for (uint32_t j = lane; j < p.topn; j += 32) { oid[j] = EMPTY_ID; if (od) od[j] = INFINITY; }
+            if (lane == 0) {
+                if (p.out_counts) p.out_counts[qi] = 0;
+                if (p.out_hops) p.out_hops[qi] = 0;
+                if (p.out_evals) p.out_evals[qi] = 0;
+                if (p.out_flags) p.out_flags[qi] = 1u;
+                if (p.out_nbrs) p.out_nbrs[qi] = 0;
+            }
+            continue;
+        }
+        Q q;
+        q.init(p.L, s.qd, gl);
+        SearchCounters cnt{0u, 1u, 0u, 0u};
+        float d0 = q.dist(p.rec + (size_t)p.ep * p.L.stride, gl, gbase);
+        RegList<KPL> L;
+        L.reset();
+        if (lane == 0) L.k[0] = make_key(d0, p.ep);
+        for (uint32_t layer = p.n_layers - 1; layer >= 1; --layer)
+            search_layer_reg<Q, KPL>(q, p.rec, p.L.stride, p.g, layer, s, L, 1, lane, cnt);
+        search_layer_reg<Q, KPL>(q, p.rec, p.L.stride, p.g, 0u, s, L, (int)p.ef, lane, cnt);
+        const uint32_t n = (uint32_t)L.count();
+        const uint32_t got = min(n, p.topn);
+#pragma unroll
+        for (int t = 0; t < KPL; ++t) {
+            uint32_t pos = (uint32_t)lane * KPL + t;
+            if (pos < p.topn) {
+                u64 k = L.k[t];
+                bool real = k != SENTINEL;
+                oid[pos] = real ? (uint32_t)(k & ~EXP_FLAG) : EMPTY_ID;
+                if (od) od[pos] = real ? __uint_as_float((uint32_t)(k >> 32)) : INFINITY;
+            }
+        }
+        for (uint32_t j = 32 * KPL + lane; j < p.topn; j += 32) { oid[j] = EMPTY_ID; if (od) od[j] = INFINITY; }
+        if (lane == 0) {
+            if (p.out_counts) p.out_counts[qi] = got;
+            if (p.out_hops) p.out_hops[qi] = cnt.hops;
+            if (p.out_evals) p.out_evals[qi] = cnt.evals;
+            if (p.out_flags) p.out_flags[qi] = cnt.overflow ? 2u : 0u;
+            if (p.out_nbrs) p.out_nbrs[qi] = cnt.nbrs;
+        }
+    }
+}
+
+template <class Q, int KPL>
+static cudaError_t launch_fast(const SearchParams& p, int num_sms, cudaStream_t st) {
+    size_t smem = fast_warp_smem(p.tbits, p.qd_cap) * SEARCH_WPB;
+    cudaError_t e = cudaFuncSetAttribute(search_fast_kernel<Q, KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, search_fast_kernel<Q, KPL>, SEARCH_WPB * 32, smem);
+    if (e != cudaSuccess) return e;
+    if (occ < 1) occ = 1;
+    uint64_t want = ((uint64_t)p.nq + SEARCH_WPB - 1) / SEARCH_WPB;
+    uint64_t cap = (uint64_t)num_sms * occ;
+    int grid = (int)(want < cap ? want : cap);
+    search_fast_kernel<Q, KPL><<<grid, SEARCH_WPB * 32, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
 uint32_t choose_vis_slots(uint32_t ef, uint32_t S0) {
     // observed: evaluations per query ~ 0.45 * ef * S0 (+ tail); keep the load factor <= ~0.6
     uint64_t want = (uint64_t)ef * (S0 ? S0 : 32);
@@ -384,6 +477,33 @@ cudaError_t launch_search(const SearchLaunch& a, int num_sms, cudaStream_t st) {
     p.out_ids = a.out_ids; p.out_dists = a.out_dists; p.out_counts = a.out_counts;
     p.out_hops = a.out_hops; p.out_evals = a.out_evals; p.out_flags = a.out_flags; p.out_nbrs = a.out_nbrs;
     p.work_counter = a.work_counter;
+    cudaError_t e = cudaMemsetAsync(a.work_counter, 0, sizeof(uint32_t), st);
+    if (e != cudaSuccess) return e;
+    // ---- fast path: list in registers (ef <= 256), 16-bit visited entries ----
+    {
+        uint32_t bbits = 1;
+        while (bbits < 31 && (1ull << bbits) < (uint64_t)a.n_points) ++bbits;
+        // table sized for a load factor around 0.25 at the mean number of evaluations (~0.35*ef*S0)
+        uint64_t want = (uint64_t)a.ef * (a.g.S0 ? a.g.S0 : 32) * 3 / 2;
+        uint32_t tbits = 9;
+        while ((1ull << tbits) < want && tbits < 15) ++tbits;
+        if (const char* ev = getenv("HNSWB200_VIS_SLOTS")) {
+            uint32_t v = (uint32_t)strtoul(ev, nullptr, 10);
+            if (v >= 64 && (v & (v - 1)) == 0) { tbits = 0; while ((1u << tbits) < v) ++tbits; }
+        }
+        if (bbits < tbits) bbits = tbits;
+        if (bbits > tbits + 12 && bbits - 12 <= 15) tbits = bbits - 12;
+        const bool fits = bbits <= tbits + 12 && fast_warp_smem(tbits, p.qd_cap) * SEARCH_WPB <= 200 * 1024;
+        if (a.ef <= 256 && fits && !getenv("HNSWB200_GENERAL_PATH")) {
+            p.tbits = tbits;
+            p.bbits = bbits;
+            HB_DISPATCH_DIM(a.L, {
+                if (a.ef <= 64) return launch_fast<Q, 2>(p, num_sms, st);
+                if (a.ef <= 128) return launch_fast<Q, 4>(p, num_sms, st);
+                return launch_fast<Q, 8>(p, num_sms, st);
+            });
+        }
+    }
     size_t per_warp = search_warp_smem(p.ef_cap, p.vis_slots, p.qd_cap);
     // shrink the visited table if one warp would not fit (overflow fallback keeps results exact)
     while (per_warp * SEARCH_WPB > 200 * 1024 && p.vis_slots > 1024) {
@@ -392,8 +512,6 @@ cudaError_t launch_search(const SearchLaunch& a, int num_sms, cudaStream_t st) {
     }
     size_t smem = per_warp * SEARCH_WPB;
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
-    cudaError_t e = cudaMemsetAsync(a.work_counter, 0, sizeof(uint32_t), st);
-    if (e != cudaSuccess) return e;
     HB_DISPATCH_DIM(a.L, {
         e = cudaFuncSetAttribute(search_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;

@@ -22,6 +22,7 @@ struct SearchLaunch {
     RecLayout L;
     DevGraph g;
     uint32_t ep;
+    uint64_t n_points;     // ids are < n_points (sizes the 16-bit visited table)
     const float* queries;  // device, nq * dim
     uint32_t nq, topn, ef;
     uint32_t vis_slots;    // 0 = choose from ef and the layer-0 row width

@@ -200,6 +200,47 @@ def test_search_synthetic(H, oracle, dim, n, m, efc):
     check_search(H, oracle, orc, queries, 3, 50)
 
 
+def test_search_general_path_matches_fast_path(H, oracle, glove, glove_index, monkeypatch):
+    """ef <= 256 normally runs the register-list / 16-bit-visited kernel; the shared-memory-list kernel
+    (used for larger ef) must give the same answers and counters."""
+    _, queries = glove
+    ix = to_gpu(H, glove_index)
+    fast = ix.ann_batch(queries, 10, 100, with_stats=True)
+    monkeypatch.setenv("HNSWB200_GENERAL_PATH", "1")
+    gen = ix.ann_batch(queries, 10, 100, with_stats=True)
+    monkeypatch.delenv("HNSWB200_GENERAL_PATH")
+    orc = glove_index.search_batch(queries, 10, 100)
+    for r in (fast, gen):
+        assert np.array_equal(r[0], orc[0]) and np.array_equal(bits(r[1]), bits(orc[1]))
+        assert np.array_equal(r[3]["hops"], orc[3]) and np.array_equal(r[3]["evals"], orc[4])
+    for ef in (64, 65, 128, 129, 256, 257):  # KPL boundaries of the register list
+        a = ix.ann_batch(queries, 10, ef, with_stats=True)
+        o = glove_index.search_batch(queries, 10, ef)
+        assert np.array_equal(a[0], o[0]) and np.array_equal(bits(a[1]), bits(o[1]))
+        assert np.array_equal(a[3]["hops"], o[3]) and np.array_equal(a[3]["evals"], o[4])
+    for n in (1, 33, 100, 300):  # more results than list registers / than ef
+        a = ix.ann_batch(queries[:20], n, 50)
+        o = glove_index.search_batch(queries[:20], n, 50)
+        assert np.array_equal(a[0], o[0]) and np.array_equal(a[2], o[2])
+
+
+@pytest.mark.parametrize("general", [False, True])
+def test_search_visited_overflow_both_paths(H, oracle, glove, glove_index, monkeypatch, general):
+    _, queries = glove
+    ix = to_gpu(H, glove_index)
+    monkeypatch.setenv("HNSWB200_VIS_SLOTS", "64")
+    if general:
+        monkeypatch.setenv("HNSWB200_GENERAL_PATH", "1")
+    ids, dists, counts, st = ix.ann_batch(queries, 10, 100, with_stats=True)
+    monkeypatch.delenv("HNSWB200_VIS_SLOTS")
+    if general:
+        monkeypatch.delenv("HNSWB200_GENERAL_PATH")
+    oids, odists, ocounts, _, oevals = glove_index.search_batch(queries, 10, 100)
+    assert (st["flags"] & 2).any()
+    assert np.array_equal(ids, oids) and np.array_equal(bits(dists), bits(odists))
+    assert (st["evals"] >= oevals).all()
+
+
 def test_search_visited_overflow_keeps_results_exact(H, oracle, glove, glove_index, monkeypatch):
     _, queries = glove
     ix = to_gpu(H, glove_index)
