@@ -28,7 +28,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-EF_SWEEP = [10, 20, 40, 80, 100, 160, 320, 640]
+EF_SWEEP = [10, 20, 40, 48, 56, 64, 72, 80, 100, 160, 320, 640]  # BASELINE's sweep plus steps between 40 and 80
 K = 10
 
 
@@ -321,7 +321,7 @@ def main():
         traffic = json.load(open(os.path.join(ROOT, "profiles", "search_kernel_traffic.json"))).get("dram_bytes_per_launch")
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "hb::search_kernel<RegQuery<12,4>>", "achieved": round(achieved, 1),
+    roofline = {"bound": "hbm", "kernel": "hb::search_kernel<RegQuery<12,4>,Vis16,4>", "achieved": round(achieved, 1),
                 "peak": peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                 "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
                 "algorithmic_bytes_per_launch": ab, "kernel_ms": round(kern_ms, 4),

@@ -715,7 +715,6 @@ int hnswb200_search_dev(hnswb200_ctx* c, const hnswb200_index* ix, const float* 
     a.nq = (uint32_t)nq;
     a.topn = n;
     a.ef = ef;
-    a.vis_slots = 0;
     a.out_ids = d_out_ids;
     a.out_dists = d_out_dists;
     a.out_counts = d_out_counts;

@@ -67,7 +67,7 @@ struct BuildParams {
     const uint8_t* job_levels;  // [njobs]
     uint32_t njobs;
     uint32_t ef_cons, m;
-    uint32_t vis_slots, ef_cap, cand_cap, m_cap, qd_cap;
+    uint32_t kpl, tbits, bbits, cand_cap, m_cap, qd_cap;
     uint32_t* out_ids;   // [njobs][n_layers][m]
     float* out_dists;    // [njobs][n_layers][m]
     uint32_t* out_cnt;   // [njobs][n_layers]
@@ -77,25 +77,34 @@ struct BuildParams {
 
 constexpr int BUILD_WPB = 2;
 
+template <class VIS>
 __host__ __device__ inline size_t build_warp_smem(const BuildParams& p) {
-    return (size_t)p.ef_cap * 8 + (size_t)p.cand_cap * 8 + (size_t)p.m_cap * 16 + (size_t)p.vis_slots * 4 + 128 +
+    return (size_t)32 * p.kpl * 8 + (size_t)p.cand_cap * 8 + (size_t)p.m_cap * 16 + VIS::bytes(p.tbits) + 128 +
            (size_t)p.qd_cap * 8;
+}
+__device__ __forceinline__ void make_vis(Vis16& v, unsigned char* mem, const BuildParams& p) {
+    v.words = reinterpret_cast<uint32_t*>(mem);
+    v.tbits = p.tbits;
+    v.bbits = p.bbits;
+}
+__device__ __forceinline__ void make_vis(Vis32& v, unsigned char* mem, const BuildParams& p) {
+    v.tab = reinterpret_cast<uint32_t*>(mem);
+    v.tbits = p.tbits;
 }
 
 // One pass of extend_candidates_with_neighbors (results.rs:122-146) restricted to keys
 // > lower: candidates <- {selected} U {Dist(n, d(point, n)) : s in selected, n in N(s)},
 // kept as the cand_cap smallest in `cand` (sorted).  Returns true if something was dropped.
-template <class Q>
+template <class Q, class VIS>
 __device__ __forceinline__ bool heuristic_fill(const Q& query, const uint8_t* __restrict__ rec,
                                                uint32_t rec_stride, const GraphView& g, uint32_t layer,
                                                const u64* list, int n, u64* cand, int& cn, int cand_cap,
-                                               u64 lower, bool have_lower, uint32_t* vis, uint32_t slots,
+                                               u64 lower, bool have_lower, const VIS& vis,
                                                uint32_t* newbuf, int lane, uint32_t& evals) {
     const int gl = lane & 3, gbase = lane & ~3, grp = lane >> 2;
-    const uint32_t vmask = slots - 1, vshift = 32 - (31 - __clz(slots));
     bool dropped = false;
     cn = 0;
-    vis_clear(vis, slots, lane);
+    vis.clear(lane);
     // the old selected set itself (select_setup, results.rs:105-111)
     for (int i = 0; i < n; ++i) {
         u64 k = list[i] & KEY_MASK;
@@ -108,7 +117,7 @@ __device__ __forceinline__ bool heuristic_fill(const Q& query, const uint8_t* __
     }
     {
         bool ovf = false;
-        for (int i = lane; i < n; i += 32) vis_insert(vis, vmask, vshift, (uint32_t)(list[i] & KEY_MASK), &ovf);
+        for (int i = lane; i < n; i += 32) vis.insert((uint32_t)(list[i] & KEY_MASK), &ovf);
         __syncwarp();
     }
     for (int si = 0; si < n; ++si) {
@@ -132,7 +141,7 @@ __device__ __forceinline__ bool heuristic_fill(const Q& query, const uint8_t* __
                 // table window is full the id is simply evaluated again (duplicate keys are
                 // skipped by the consumer).
                 bool ovf = false;
-                bool isnew = valid && vis_insert(vis, vmask, vshift, nb, &ovf);
+                bool isnew = valid && vis.insert(nb, &ovf);
                 unsigned nm = __ballot_sync(HB_FULL, isnew);
                 int ncnt = __popc(nm);
                 if (ncnt == 0) continue;
@@ -171,16 +180,16 @@ __device__ __forceinline__ bool heuristic_fill(const Q& query, const uint8_t* __
 
 // Searcher::select_heuristic(m, extend_cands = true, keep_pruned = true)
 // (searcher.rs:109-153).  On exit list[0..n) is the new selected set, sorted.
-template <class Q>
+template <class Q, class VIS>
 __device__ __forceinline__ void select_heuristic(const Q& query, const BuildParams& p, uint32_t layer,
                                                  u64* list, int& n, u64* cand, u64* sel, u64* rej,
-                                                 uint32_t* vis, uint32_t* newbuf, float* qd2, int lane,
+                                                 const VIS& vis, uint32_t* newbuf, float* qd2, int lane,
                                                  uint32_t& evals) {
     const int gl = lane & 3, gbase = lane & ~3, grp = lane >> 2;
     const int m = (int)p.m;
     int cn = 0, ci = 0, sn = 0, rn = 0;
     bool dropped = heuristic_fill(query, p.rec, p.L.stride, p.g, layer, list, n, cand, cn, (int)p.cand_cap,
-                                  0ull, false, vis, p.vis_slots, newbuf, lane, evals);
+                                  0ull, false, vis, newbuf, lane, evals);
     u64 last = 0;
     bool first = true;
     while (sn < m) {
@@ -188,7 +197,7 @@ __device__ __forceinline__ void select_heuristic(const Q& query, const BuildPara
             if (!dropped) break;  // candidates exhausted
             // the bounded window ran dry: refill it with the next smallest keys > last
             dropped = heuristic_fill(query, p.rec, p.L.stride, p.g, layer, list, n, cand, cn, (int)p.cand_cap,
-                                     last, true, vis, p.vis_slots, newbuf, lane, evals);
+                                     last, true, vis, newbuf, lane, evals);
             ci = 0;
             if (cn == 0) break;
         }
@@ -243,23 +252,25 @@ __device__ __forceinline__ void select_heuristic(const Q& query, const BuildPara
     __syncwarp();
 }
 
-template <class Q>
+template <class Q, class VIS>
 __global__ void __launch_bounds__(BUILD_WPB * 32) build_kernel(BuildParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int gl = lane & 3, gbase = lane & ~3;
-    unsigned char* wsm = smem + (size_t)wib * build_warp_smem(p);
-    u64* list = reinterpret_cast<u64*>(wsm);
-    u64* cand = list + p.ef_cap;
+    unsigned char* wsm = smem + (size_t)wib * build_warp_smem<VIS>(p);
+    KeyList<0> L;
+    L.list = reinterpret_cast<u64*>(wsm);
+    L.kpl = (int)p.kpl;
+    u64* list = L.list;
+    u64* cand = list + 32 * p.kpl;
     u64* sel = cand + p.cand_cap;
     u64* rej = sel + p.m_cap;
-    WarpScratch s;
-    s.list = list;
-    s.vis = reinterpret_cast<uint32_t*>(rej + p.m_cap);
-    s.newbuf = s.vis + p.vis_slots;
-    s.qd = reinterpret_cast<float*>(s.newbuf + 32);
-    s.vis_slots = p.vis_slots;
-    float* qd2 = s.qd + p.qd_cap;
+    unsigned char* vmem = reinterpret_cast<unsigned char*>(rej + p.m_cap);
+    VIS vis;
+    make_vis(vis, vmem, p);
+    uint32_t* newbuf = reinterpret_cast<uint32_t*>(vmem + VIS::bytes(p.tbits));
+    float* qd = reinterpret_cast<float*>(newbuf + 32);
+    float* qd2 = qd + p.qd_cap;
 
     while (true) {
         uint32_t j = 0;
@@ -275,24 +286,27 @@ __global__ void __launch_bounds__(BUILD_WPB * 32) build_kernel(BuildParams p) {
             continue;
         }
         __syncwarp();
-        warp_dequant_record(p.L, p.rec + (size_t)pid * p.L.stride, lane, s.qd);
+        warp_dequant_record(p.L, p.rec + (size_t)pid * p.L.stride, lane, qd);
         __syncwarp();
         Q q;
-        q.init(p.L, s.qd, gl);
+        q.init(p.L, qd, gl);
         SearchCounters cnt{0u, 1u, 0u, 0u};
         // setup_insert (inserter.rs:53-68): selected <- {Dist(ep, distance(ep, id))}
         float d0 = q.dist(p.rec + (size_t)p.ep * p.L.stride, gl, gbase);
+        L.reset(lane);
         if (lane == 0) list[0] = make_key(d0, p.ep);
         __syncwarp();
-        int n = 1;
         // traverse_layers_above (inserter.rs:70-89)
         for (uint32_t layer = p.n_layers - 1; layer > level; --layer)
-            search_layer(q, p.rec, p.L.stride, p.g, layer, s, n, 1, lane, cnt);
+            search_layer<Q, VIS, 0>(q, p.rec, p.L.stride, p.g, layer, L, vis, newbuf, 1, lane, cnt);
         // traverse_layers_below (inserter.rs:91-126)
         uint32_t bound = min(level, p.n_layers - 1);
         for (uint32_t layer = bound + 1; layer-- > 0;) {
-            search_layer(q, p.rec, p.L.stride, p.g, layer, s, n, (int)p.ef_cons, lane, cnt);
-            select_heuristic(q, p, layer, list, n, cand, sel, rej, s.vis, s.newbuf, qd2, lane, cnt.evals);
+            search_layer<Q, VIS, 0>(q, p.rec, p.L.stride, p.g, layer, L, vis, newbuf, (int)p.ef_cons, lane, cnt);
+            int n = list_count(list, (int)p.ef_cons, lane);
+            select_heuristic<Q, VIS>(q, p, layer, list, n, cand, sel, rej, vis, newbuf, qd2, lane, cnt.evals);
+            // the heuristic's picks are the entry set of the next layer: restore the sentinel tail
+            for (int i = n + lane; i < 32 * (int)p.kpl; i += 32) list[i] = SENTINEL;
             // save_layer_results (results.rs:79-84)
             uint32_t* oi = p.out_ids + ((size_t)j * p.n_layers + layer) * p.m;
             float* od = p.out_dists + ((size_t)j * p.n_layers + layer) * p.m;
@@ -536,13 +550,15 @@ int build_insert(hnswb200_ctx* c, hnswb200_index* ix, const std::vector<uint32_t
     p.ep = prm.ep;
     p.ef_cons = (uint32_t)prm.ef_cons;
     p.m = m;
-    p.ef_cap = (p.ef_cons + 1) / 2 * 2;
-    p.cand_cap = std::max<uint32_t>(256, p.ef_cap);
+    p.kpl = ((std::max<uint32_t>(p.ef_cons, m) + 31) / 32 + 1) / 2 * 2;
+    p.cand_cap = std::max<uint32_t>(256, 32 * p.kpl);
     p.m_cap = (m + 1) / 2 * 2;
     p.qd_cap = (p.L.dim + 7) / 8 * 8 + 8;
-    p.vis_slots = choose_vis_slots(p.ef_cons, h.a0.S);
-    while (build_warp_smem(p) * BUILD_WPB > 200 * 1024 && p.vis_slots > 1024) p.vis_slots >>= 1;
-    const size_t smem = build_warp_smem(p) * BUILD_WPB;
+    bool use16;
+    choose_visited(p.ef_cons, h.a0.S, h.n_points(), &p.tbits, &p.bbits, &use16);
+    auto bytes = [&]() { return (use16 ? build_warp_smem<Vis16>(p) : build_warp_smem<Vis32>(p)) * BUILD_WPB; };
+    while (bytes() > 200 * 1024 && p.tbits > 9 && (!use16 || p.bbits <= p.tbits - 1 + 12)) --p.tbits;
+    const size_t smem = bytes();
     if (smem > 227 * 1024) return (set_error("build: ef_cons too large for the shared-memory working set"), HNSWB200_EINVAL);
 
     DevBuf<uint32_t> d_jobs, d_oids, d_ocnt, d_oev;
@@ -567,9 +583,14 @@ int build_insert(hnswb200_ctx* c, hnswb200_index* ix, const std::vector<uint32_t
 
     int grid_cap = 0;
     HB_DISPATCH_DIM_B(p.L, {
-        HB_CUDA(cudaFuncSetAttribute(build_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int occ = 0;
-        HB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, build_kernel<Q>, BUILD_WPB * 32, smem));
+        if (use16) {
+            HB_CUDA(cudaFuncSetAttribute(build_kernel<Q, Vis16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            HB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, build_kernel<Q, Vis16>, BUILD_WPB * 32, smem));
+        } else {
+            HB_CUDA(cudaFuncSetAttribute(build_kernel<Q, Vis32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            HB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, build_kernel<Q, Vis32>, BUILD_WPB * 32, smem));
+        }
         grid_cap = c->num_sms * (occ < 1 ? 1 : occ);
     });
 
@@ -601,7 +622,10 @@ int build_insert(hnswb200_ctx* c, hnswb200_index* ix, const std::vector<uint32_t
         HB_CUDA(cudaMemcpyAsync(d_jlv.p, jl.data(), nb, cudaMemcpyHostToDevice, c->stream));
         HB_CUDA(cudaMemsetAsync(c->d_scratch, 0, 4, c->stream));
         int grid = std::min<int>(grid_cap, (int)((nb + BUILD_WPB - 1) / BUILD_WPB));
-        HB_DISPATCH_DIM_B(p.L, { build_kernel<Q><<<grid, BUILD_WPB * 32, smem, c->stream>>>(p); });
+        HB_DISPATCH_DIM_B(p.L, {
+            if (use16) build_kernel<Q, Vis16><<<grid, BUILD_WPB * 32, smem, c->stream>>>(p);
+            else build_kernel<Q, Vis32><<<grid, BUILD_WPB * 32, smem, c->stream>>>(p);
+        });
         HB_CUDA(cudaGetLastError());
         HB_CUDA(cudaMemcpyAsync(o_ids.data(), d_oids.p, (size_t)nb * nl * m * 4, cudaMemcpyDeviceToHost, c->stream));
         HB_CUDA(cudaMemcpyAsync(o_d.data(), d_od.p, (size_t)nb * nl * m * 4, cudaMemcpyDeviceToHost, c->stream));

@@ -13,7 +13,6 @@
 
 #include "kernels.h"
 #include "search.cuh"
-#include "search_reg.cuh"
 
 namespace hb {
 
@@ -272,9 +271,10 @@ struct SearchParams {
     GraphView g;
     uint32_t n_layers, ep;
     const float* queries;
-    uint32_t nq, topn, ef, vis_slots;
-    uint32_t ef_cap, qd_cap;
-    uint32_t tbits, bbits;  // fast path: 16-bit visited table geometry
+    uint32_t nq, topn, ef;
+    uint32_t kpl;           // keys per lane of the result list (capacity 32*kpl >= ef)
+    uint32_t tbits, bbits;  // visited table: 2^tbits entries; ids < 2^bbits
+    uint32_t qd_cap;
     uint32_t* out_ids;
     float* out_dists;
     uint32_t* out_counts;
@@ -287,22 +287,34 @@ struct SearchParams {
 
 constexpr int SEARCH_WPB = 4;
 
-__host__ __device__ inline size_t search_warp_smem(uint32_t ef_cap, uint32_t vis_slots, uint32_t qd_cap) {
-    return (size_t)ef_cap * 8 + (size_t)vis_slots * 4 + 128 + (size_t)qd_cap * 4;
+template <class VIS>
+__host__ __device__ inline size_t search_warp_smem(uint32_t kpl, uint32_t tbits, uint32_t qd_cap) {
+    return (size_t)32 * kpl * 8 + VIS::bytes(tbits) + 128 + (size_t)qd_cap * 4;
 }
 
-template <class Q>
+__device__ __forceinline__ void make_vis(Vis16& v, unsigned char* mem, const SearchParams& p) {
+    v.words = reinterpret_cast<uint32_t*>(mem);
+    v.tbits = p.tbits;
+    v.bbits = p.bbits;
+}
+__device__ __forceinline__ void make_vis(Vis32& v, unsigned char* mem, const SearchParams& p) {
+    v.tab = reinterpret_cast<uint32_t*>(mem);
+    v.tbits = p.tbits;
+}
+
+template <class Q, class VIS, int KPL>
 __global__ void __launch_bounds__(SEARCH_WPB * 32) search_kernel(SearchParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int gl = lane & 3, gbase = lane & ~3;
-    unsigned char* wsm = smem + (size_t)wib * search_warp_smem(p.ef_cap, p.vis_slots, p.qd_cap);
-    WarpScratch s;
-    s.list = reinterpret_cast<u64*>(wsm);
-    s.vis = reinterpret_cast<uint32_t*>(wsm + (size_t)p.ef_cap * 8);
-    s.newbuf = s.vis + p.vis_slots;
-    s.qd = reinterpret_cast<float*>(s.newbuf + 32);
-    s.vis_slots = p.vis_slots;
+    unsigned char* wsm = smem + (size_t)wib * search_warp_smem<VIS>(p.kpl, p.tbits, p.qd_cap);
+    KeyList<KPL> L;
+    L.list = reinterpret_cast<u64*>(wsm);
+    L.kpl = (int)p.kpl;
+    VIS vis;
+    make_vis(vis, wsm + (size_t)32 * p.kpl * 8, p);
+    uint32_t* newbuf = reinterpret_cast<uint32_t*>(wsm + (size_t)32 * p.kpl * 8 + VIS::bytes(p.tbits));
+    float* qd = reinterpret_cast<float*>(newbuf + 32);
 
     while (true) {
         uint32_t qi = 0;
@@ -312,7 +324,7 @@ __global__ void __launch_bounds__(SEARCH_WPB * 32) search_kernel(SearchParams p)
         __syncwarp();
         // Point::new(vector): the query is quantised exactly like a stored point (template.rs:313)
         float mn, dl;
-        bool ok = warp_quantise(p.queries + (size_t)qi * p.L.dim, p.L.dim, lane, s.qd, nullptr, mn, dl);
+        bool ok = warp_quantise(p.queries + (size_t)qi * p.L.dim, p.L.dim, lane, qd, nullptr, mn, dl);
         __syncwarp();
         uint32_t* oid = p.out_ids + (size_t)qi * p.topn;
         float* od = p.out_dists ? p.out_dists + (size_t)qi * p.topn : nullptr;
@@ -328,27 +340,27 @@ __global__ void __launch_bounds__(SEARCH_WPB * 32) search_kernel(SearchParams p)
             continue;
         }
         Q q;
-        q.init(p.L, s.qd, gl);
+        q.init(p.L, qd, gl);
         SearchCounters cnt{0u, 1u, 0u, 0u};
         // selected <- {Dist(ep, distance2point(point, ep))}   (template.rs:316-319)
         float d0 = q.dist(p.rec + (size_t)p.ep * p.L.stride, gl, gbase);
-        if (lane == 0) s.list[0] = make_key(d0, p.ep);
+        L.reset(lane);
+        if (lane == 0) L.list[0] = make_key(d0, p.ep);
         __syncwarp();
-        int n = 1;
         for (uint32_t layer = p.n_layers - 1; layer >= 1; --layer)  // template.rs:322-324
-            search_layer(q, p.rec, p.L.stride, p.g, layer, s, n, 1, lane, cnt);
-        search_layer(q, p.rec, p.L.stride, p.g, 0u, s, n, (int)p.ef, lane, cnt);  // template.rs:326
+            search_layer<Q, VIS, KPL>(q, p.rec, p.L.stride, p.g, layer, L, vis, newbuf, 1, lane, cnt);
+        search_layer<Q, VIS, KPL>(q, p.rec, p.L.stride, p.g, 0u, L, vis, newbuf, (int)p.ef, lane, cnt);  // :326
         // get_top_selected(n)   (results.rs:59-61)
-        uint32_t got = min((uint32_t)n, p.topn);
-        for (uint32_t j = lane; j < p.topn; j += 32) {
-            if (j < got) {
-                u64 k = s.list[j];
-                oid[j] = (uint32_t)k;
-                if (od) od[j] = __uint_as_float((uint32_t)(k >> 32));
-            } else {
-                oid[j] = EMPTY_ID;
-                if (od) od[j] = INFINITY;
+        uint32_t got = 0;
+        for (uint32_t j0 = 0; j0 < p.topn; j0 += 32) {
+            uint32_t j = j0 + lane;
+            u64 k = (j < p.topn && j < p.ef) ? L.list[j] : SENTINEL;
+            bool real = k != SENTINEL;
+            if (j < p.topn) {
+                oid[j] = real ? (uint32_t)k : EMPTY_ID;
+                if (od) od[j] = real ? __uint_as_float((uint32_t)(k >> 32)) : INFINITY;
             }
+            got += __popc(__ballot_sync(HB_FULL, real));
         }
         if (lane == 0) {
             if (p.out_counts) p.out_counts[qi] = got;
@@ -360,103 +372,52 @@ __global__ void __launch_bounds__(SEARCH_WPB * 32) search_kernel(SearchParams p)
     }
 }
 
-
-// Fast path: register-resident list (KPL keys per lane), 16-bit visited table.
-__host__ __device__ inline size_t fast_warp_smem(uint32_t tbits, uint32_t qd_cap) {
-    return ((size_t)2 << tbits) + 128 + (size_t)qd_cap * 4;
-}
-
-template <class Q, int KPL>
-__global__ void __launch_bounds__(SEARCH_WPB * 32) search_fast_kernel(SearchParams p) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int gl = lane & 3, gbase = lane & ~3;
-    unsigned char* wsm = smem + (size_t)wib * fast_warp_smem(p.tbits, p.qd_cap);
-    WarpScratch16 s;
-    s.vis.words = reinterpret_cast<uint32_t*>(wsm);
-    s.vis.tbits = p.tbits;
-    s.vis.bbits = p.bbits;
-    s.vis.bmask = (p.bbits >= 32) ? 0xFFFFFFFFu : ((1u << p.bbits) - 1u);
-    s.newbuf = reinterpret_cast<uint32_t*>(wsm + ((size_t)2 << p.tbits));
-    s.qd = reinterpret_cast<float*>(s.newbuf + 32);
-
-    while (true) {
-        uint32_t qi = 0;
-        if (lane == 0) qi = atomicAdd(p.work_counter, 1u);
-        qi = __shfl_sync(HB_FULL, qi, 0);
-        if (qi >= p.nq) break;
-        __syncwarp();
-        float mn, dl;
-        bool ok = warp_quantise(p.queries + (size_t)qi * p.L.dim, p.L.dim, lane, s.qd, nullptr, mn, dl);
-        __syncwarp();
-        uint32_t* oid = p.out_ids + (size_t)qi * p.topn;
-        float* od = p.out_dists ? p.out_dists + (size_t)qi * p.topn : nullptr;
-        if (!ok) {
-            for (uint32_t j = lane; j < p.topn; j += 32) { oid[j] = EMPTY_ID; if (od) od[j] = INFINITY; }
-            if (lane == 0) {
-                if (p.out_counts) p.out_counts[qi] = 0;
-                if (p.out_hops) p.out_hops[qi] = 0;
-                if (p.out_evals) p.out_evals[qi] = 0;
-                if (p.out_flags) p.out_flags[qi] = 1u;
-                if (p.out_nbrs) p.out_nbrs[qi] = 0;
-            }
-            continue;
-        }
-        Q q;
-        q.init(p.L, s.qd, gl);
-        SearchCounters cnt{0u, 1u, 0u, 0u};
-        float d0 = q.dist(p.rec + (size_t)p.ep * p.L.stride, gl, gbase);
-        RegList<KPL> L;
-        L.reset();
-        if (lane == 0) L.k[0] = make_key(d0, p.ep);
-        for (uint32_t layer = p.n_layers - 1; layer >= 1; --layer)
-            search_layer_reg<Q, KPL>(q, p.rec, p.L.stride, p.g, layer, s, L, 1, lane, cnt);
-        search_layer_reg<Q, KPL>(q, p.rec, p.L.stride, p.g, 0u, s, L, (int)p.ef, lane, cnt);
-        const uint32_t n = (uint32_t)L.count();
-        const uint32_t got = min(n, p.topn);
-#pragma unroll
-        for (int t = 0; t < KPL; ++t) {
-            uint32_t pos = (uint32_t)lane * KPL + t;
-            if (pos < p.topn) {
-                u64 k = L.k[t];
-                bool real = k != SENTINEL;
-                oid[pos] = real ? (uint32_t)(k & ~EXP_FLAG) : EMPTY_ID;
-                if (od) od[pos] = real ? __uint_as_float((uint32_t)(k >> 32)) : INFINITY;
-            }
-        }
-        for (uint32_t j = 32 * KPL + lane; j < p.topn; j += 32) { oid[j] = EMPTY_ID; if (od) od[j] = INFINITY; }
-        if (lane == 0) {
-            if (p.out_counts) p.out_counts[qi] = got;
-            if (p.out_hops) p.out_hops[qi] = cnt.hops;
-            if (p.out_evals) p.out_evals[qi] = cnt.evals;
-            if (p.out_flags) p.out_flags[qi] = cnt.overflow ? 2u : 0u;
-            if (p.out_nbrs) p.out_nbrs[qi] = cnt.nbrs;
-        }
+template <class Q, class VIS, int KPL>
+static cudaError_t launch_search_t(const SearchParams& p, int num_sms, cudaStream_t st) {
+    size_t smem = search_warp_smem<VIS>(p.kpl, p.tbits, p.qd_cap) * SEARCH_WPB;
+    if (smem > 227 * 1024) return cudaErrorInvalidValue;
+    static int occ_cache = 0;
+    static size_t occ_smem = 0;
+    cudaError_t e;
+    if (occ_cache == 0 || occ_smem != smem) {
+        e = cudaFuncSetAttribute(search_kernel<Q, VIS, KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        int occ = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, search_kernel<Q, VIS, KPL>, SEARCH_WPB * 32, smem);
+        if (e != cudaSuccess) return e;
+        occ_cache = occ < 1 ? 1 : occ;
+        occ_smem = smem;
     }
-}
-
-template <class Q, int KPL>
-static cudaError_t launch_fast(const SearchParams& p, int num_sms, cudaStream_t st) {
-    size_t smem = fast_warp_smem(p.tbits, p.qd_cap) * SEARCH_WPB;
-    cudaError_t e = cudaFuncSetAttribute(search_fast_kernel<Q, KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    int occ = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, search_fast_kernel<Q, KPL>, SEARCH_WPB * 32, smem);
-    if (e != cudaSuccess) return e;
-    if (occ < 1) occ = 1;
     uint64_t want = ((uint64_t)p.nq + SEARCH_WPB - 1) / SEARCH_WPB;
-    uint64_t cap = (uint64_t)num_sms * occ;
+    uint64_t cap = (uint64_t)num_sms * occ_cache;
     int grid = (int)(want < cap ? want : cap);
-    search_fast_kernel<Q, KPL><<<grid, SEARCH_WPB * 32, smem, st>>>(p);
+    search_kernel<Q, VIS, KPL><<<grid, SEARCH_WPB * 32, smem, st>>>(p);
     return cudaGetLastError();
 }
 
-uint32_t choose_vis_slots(uint32_t ef, uint32_t S0) {
-    // observed: evaluations per query ~ 0.45 * ef * S0 (+ tail); keep the load factor <= ~0.6
-    uint64_t want = (uint64_t)ef * (S0 ? S0 : 32);
-    uint32_t s = 1024;
-    while (s < want && s < (1u << 20)) s <<= 1;
-    return s;
+// visited-table geometry shared by the query and the build kernels
+void choose_visited(uint32_t ef, uint32_t S0, uint64_t n_points, uint32_t* tbits, uint32_t* bbits, bool* use16) {
+    uint32_t bb = 1;
+    while (bb < 31 && (1ull << bb) < n_points) ++bb;
+    // observed: evaluations per query ~ 0.35 * ef * S0; aim at a load factor around 0.25
+    uint64_t want = (uint64_t)ef * (S0 ? S0 : 32) * 3 / 2;
+    uint32_t tb = 9;
+    while ((1ull << tb) < want && tb < 16) ++tb;
+    if (const char* ev = getenv("HNSWB200_VIS_SLOTS")) {  // test knob: force the overflow fallback
+        uint32_t v = (uint32_t)strtoul(ev, nullptr, 10);
+        if (v >= 64 && (v & (v - 1)) == 0) { tb = 0; while ((1u << tb) < v) ++tb; }
+    }
+    bool u16 = !getenv("HNSWB200_VIS32");
+    if (u16) {
+        if (bb < tb) bb = tb;
+        if (bb > tb + 12) {
+            if (bb - 12 <= 14) tb = bb - 12;  // a larger table makes the remainder fit 12 bits
+            else u16 = false;
+        }
+    }
+    *tbits = tb;
+    *bbits = bb;
+    *use16 = u16;
 }
 
 cudaError_t launch_search(const SearchLaunch& a, int num_sms, cudaStream_t st) {
@@ -467,64 +428,30 @@ cudaError_t launch_search(const SearchLaunch& a, int num_sms, cudaStream_t st) {
     p.g.adj0 = a.g.adj0; p.g.S0 = a.g.S0; p.g.upper_off = a.g.upper_off; p.g.upper_adj = a.g.upper_adj; p.g.SU = a.g.SU;
     p.n_layers = a.g.n_layers; p.ep = a.ep;
     p.queries = a.queries; p.nq = a.nq; p.topn = a.topn; p.ef = a.ef;
-    p.vis_slots = a.vis_slots ? a.vis_slots : choose_vis_slots(a.ef, a.g.S0);
-    if (const char* e = getenv("HNSWB200_VIS_SLOTS")) {  // test knob: force the overflow fallback
-        uint32_t v = (uint32_t)strtoul(e, nullptr, 10);
-        if (v >= 64 && (v & (v - 1)) == 0) p.vis_slots = v;
-    }
-    p.ef_cap = round_up(a.ef, 2);
     p.qd_cap = round_up(a.L.dim, 8) + 8;
     p.out_ids = a.out_ids; p.out_dists = a.out_dists; p.out_counts = a.out_counts;
     p.out_hops = a.out_hops; p.out_evals = a.out_evals; p.out_flags = a.out_flags; p.out_nbrs = a.out_nbrs;
     p.work_counter = a.work_counter;
+    bool use16;
+    choose_visited(a.ef, a.g.S0, a.n_points, &p.tbits, &p.bbits, &use16);
+    const bool generic_list = a.ef > 256 || getenv("HNSWB200_GENERAL_PATH");
+    p.kpl = generic_list ? round_up((a.ef + 31) / 32, 2) : (a.ef <= 128 ? 4 : 8);
+    // shrink the visited table if one block would not fit (the overflow fallback keeps results exact)
+    auto bytes = [&](uint32_t tb) {
+        return (use16 ? search_warp_smem<Vis16>(p.kpl, tb, p.qd_cap) : search_warp_smem<Vis32>(p.kpl, tb, p.qd_cap)) * SEARCH_WPB;
+    };
+    while (bytes(p.tbits) > 200 * 1024 && p.tbits > 9 && (!use16 || p.bbits <= p.tbits - 1 + 12)) --p.tbits;
     cudaError_t e = cudaMemsetAsync(a.work_counter, 0, sizeof(uint32_t), st);
     if (e != cudaSuccess) return e;
-    // ---- fast path: list in registers (ef <= 256), 16-bit visited entries ----
-    {
-        uint32_t bbits = 1;
-        while (bbits < 31 && (1ull << bbits) < (uint64_t)a.n_points) ++bbits;
-        // table sized for a load factor around 0.25 at the mean number of evaluations (~0.35*ef*S0)
-        uint64_t want = (uint64_t)a.ef * (a.g.S0 ? a.g.S0 : 32) * 3 / 2;
-        uint32_t tbits = 9;
-        while ((1ull << tbits) < want && tbits < 15) ++tbits;
-        if (const char* ev = getenv("HNSWB200_VIS_SLOTS")) {
-            uint32_t v = (uint32_t)strtoul(ev, nullptr, 10);
-            if (v >= 64 && (v & (v - 1)) == 0) { tbits = 0; while ((1u << tbits) < v) ++tbits; }
-        }
-        if (bbits < tbits) bbits = tbits;
-        if (bbits > tbits + 12 && bbits - 12 <= 15) tbits = bbits - 12;
-        const bool fits = bbits <= tbits + 12 && fast_warp_smem(tbits, p.qd_cap) * SEARCH_WPB <= 200 * 1024;
-        if (a.ef <= 256 && fits && !getenv("HNSWB200_GENERAL_PATH")) {
-            p.tbits = tbits;
-            p.bbits = bbits;
-            HB_DISPATCH_DIM(a.L, {
-                if (a.ef <= 64) return launch_fast<Q, 2>(p, num_sms, st);
-                if (a.ef <= 128) return launch_fast<Q, 4>(p, num_sms, st);
-                return launch_fast<Q, 8>(p, num_sms, st);
-            });
-        }
-    }
-    size_t per_warp = search_warp_smem(p.ef_cap, p.vis_slots, p.qd_cap);
-    // shrink the visited table if one warp would not fit (overflow fallback keeps results exact)
-    while (per_warp * SEARCH_WPB > 200 * 1024 && p.vis_slots > 1024) {
-        p.vis_slots >>= 1;
-        per_warp = search_warp_smem(p.ef_cap, p.vis_slots, p.qd_cap);
-    }
-    size_t smem = per_warp * SEARCH_WPB;
-    if (smem > 227 * 1024) return cudaErrorInvalidValue;
     HB_DISPATCH_DIM(a.L, {
-        e = cudaFuncSetAttribute(search_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        int occ = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, search_kernel<Q>, SEARCH_WPB * 32, smem);
-        if (e != cudaSuccess) return e;
-        if (occ < 1) occ = 1;
-        uint64_t want = ((uint64_t)a.nq + SEARCH_WPB - 1) / SEARCH_WPB;
-        uint64_t cap = (uint64_t)num_sms * occ;
-        int grid = (int)(want < cap ? want : cap);
-        search_kernel<Q><<<grid, SEARCH_WPB * 32, smem, st>>>(p);
+        if (use16) {
+            if (generic_list) return launch_search_t<Q, Vis16, 0>(p, num_sms, st);
+            if (p.kpl == 4) return launch_search_t<Q, Vis16, 4>(p, num_sms, st);
+            return launch_search_t<Q, Vis16, 8>(p, num_sms, st);
+        }
+        return launch_search_t<Q, Vis32, 0>(p, num_sms, st);
     });
-    return cudaGetLastError();
+    return cudaErrorUnknown;
 }
 
 // ---------------------------------------------------------------------------

@@ -25,7 +25,6 @@ struct SearchLaunch {
     uint64_t n_points;     // ids are < n_points (sizes the 16-bit visited table)
     const float* queries;  // device, nq * dim
     uint32_t nq, topn, ef;
-    uint32_t vis_slots;    // 0 = choose from ef and the layer-0 row width
     uint32_t* out_ids;     // nq * topn (EMPTY padded)
     float* out_dists;      // nq * topn (+inf padded), may be null
     uint32_t* out_counts;  // nq, may be null
@@ -60,7 +59,7 @@ cudaError_t launch_dist_one_to_many(const uint8_t* rec, const RecLayout& L, cons
 cudaError_t launch_dist_full_pairs(const float* x, const float* y, uint64_t n, uint32_t dim,
                                    float* out, cudaStream_t st);
 cudaError_t launch_search(const SearchLaunch& a, int num_sms, cudaStream_t st);
-uint32_t choose_vis_slots(uint32_t ef, uint32_t S0);
+void choose_visited(uint32_t ef, uint32_t S0, uint64_t n_points, uint32_t* tbits, uint32_t* bbits, bool* use16);
 
 // brute force: one pass over base records [b0, b1) for all queries
 cudaError_t launch_bf_chunk(const uint8_t* base_rec, const RecLayout& L, uint64_t b0, uint64_t b1,

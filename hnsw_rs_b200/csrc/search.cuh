@@ -2,21 +2,27 @@
 // the build kernel.
 //
 // Restates Searcher::search_layer (hnsw/src/template/searcher.rs:23-103) over the
-// Results sets (hnsw/src/template/results.rs:26-33) with one 32-lane CTA-slice
-// (one warp) per query:
+// Results sets (hnsw/src/template/results.rs:26-33) with one warp per query:
 //   selected    -> sorted array of u64 keys in shared memory, key =
 //                  (f32 bits of dist << 32) | id.  Non-negative f32 bit patterns
 //                  order like unsigned ints, so integer compare == Dist::cmp
-//                  (graph/src/dist.rs:30-37: dist, then id).
+//                  (graph/src/dist.rs:30-37: dist, then id).  The array has
+//                  C = 32*KPL slots; unused slots hold the sentinel ~0, so
+//                  "|selected| < ef" is the same test as key < list[ef-1].
 //   candidates  -> the not-yet-expanded members of `selected` (bit 31 of the id
-//                  half marks "expanded").  A candidate that has fallen out of
-//                  `selected` is > the worst selected, so popping it is exactly
-//                  the reference's break (searcher.rs:41-44); hence "no
-//                  unexpanded entry left" == the reference's loop exit.
-//   visited     -> open-addressing hash set of ids in shared memory.
+//                  half marks "expanded"; the sentinel has it set).  A candidate
+//                  that has fallen out of `selected` is > the worst selected, so
+//                  popping it is exactly the reference's break (searcher.rs:41-44);
+//                  hence "no unexpanded entry left" == the reference's loop exit.
+//   visited     -> exact open-addressing hash set of ids in shared memory
+//                  (Vis16: 16-bit entries for ids < 2^(t+12); Vis32: 32-bit entries).
 // Exactly one candidate is expanded per iteration; all unvisited
 // neighbours of that candidate are evaluated in parallel, 8 per round, 4 lanes
 // each, which is result- and counter-identical to the reference (App. C-5).
+//
+// List maintenance is lane-major: lane l owns slots [l*KPL, (l+1)*KPL).  A position
+// search is one pass (each lane compares its KPL keys, one ballot), an insertion is one
+// predicated store per moved key.
 #pragma once
 #include "dist.cuh"
 
@@ -26,6 +32,7 @@ constexpr uint32_t EMPTY_ID = 0xFFFFFFFFu;
 constexpr uint32_t CHAIN_BIT = 0x80000000u;  // adjacency slot: continuation row marker
 constexpr u64 EXP_FLAG = 0x80000000ull;      // list key: "expanded"
 constexpr u64 KEY_MASK = ~EXP_FLAG;
+constexpr u64 SENTINEL = ~0ull;
 
 struct GraphView {
     const uint32_t* adj0;       // layer 0: row r = node id (r < n_points) or chain row
@@ -33,14 +40,6 @@ struct GraphView {
     const uint32_t* upper_off;  // [n_points] first upper row of the node, EMPTY_ID if level 0
     const uint32_t* upper_adj;  // rows for layers >= 1: row = upper_off[node] + (layer - 1)
     uint32_t SU;                // slots per upper row
-};
-
-struct WarpScratch {
-    u64* list;          // [ef_cap]
-    uint32_t* vis;      // [vis_slots]
-    uint32_t* newbuf;   // [32]
-    float* qd;          // [dim padded]
-    uint32_t vis_slots; // power of two >= 64
 };
 
 struct SearchCounters {
@@ -54,7 +53,155 @@ __device__ __forceinline__ u64 make_key(float d, uint32_t id) {
     return ((u64)__float_as_uint(d) << 32) | (u64)id;
 }
 
-// number of list entries (masked) strictly smaller than key; list sorted ascending
+// ---------------------------------------------------------------------------
+// visited sets
+// ---------------------------------------------------------------------------
+// 32-bit entries: any id < 2^31.
+struct Vis32 {
+    uint32_t* tab;
+    uint32_t tbits;
+    static __host__ __device__ size_t bytes(uint32_t tbits) { return (size_t)4 << tbits; }
+    __device__ __forceinline__ void clear(int lane) const {
+        uint4* p = reinterpret_cast<uint4*>(tab);
+        const uint4 e = make_uint4(EMPTY_ID, EMPTY_ID, EMPTY_ID, EMPTY_ID);
+        for (uint32_t i = lane; i < (1u << tbits) / 4; i += 32) p[i] = e;
+        __syncwarp();
+    }
+    // true if id was not yet in the set (and records it).  On an exhausted probe window the
+    // id is reported new but NOT recorded and *ovf is raised; the caller then falls back to
+    // a list-membership test so results stay exact.
+    __device__ __forceinline__ bool insert(uint32_t id, bool* ovf) const {
+        const uint32_t mask = (1u << tbits) - 1u;
+        uint32_t h = (id * 0x9E3779B1u) >> (32 - tbits);
+#pragma unroll 1
+        for (int probe = 0; probe < 48; ++probe) {
+            uint32_t old = atomicCAS(&tab[h], EMPTY_ID, id);
+            if (old == EMPTY_ID) return true;
+            if (old == id) return false;
+            h = (h + 1) & mask;
+        }
+        *ovf = true;
+        return true;
+    }
+};
+
+// 16-bit entries (ids < 2^B, table of T = 2^t entries): h = (id * odd) mod 2^B is a bijection
+// on B-bit ids; home = top t bits of h, rem = low B-t bits.  An entry stores
+// (rem << 4 | displacement) with displacement <= 14, so (slot, entry) determines the id:
+// no false positives, no false negatives.  Needs B - t <= 12.
+struct Vis16 {
+    uint32_t* words;  // T/2 words holding two entries each
+    uint32_t tbits, bbits;
+    static __host__ __device__ size_t bytes(uint32_t tbits) { return (size_t)2 << tbits; }
+    __device__ __forceinline__ void clear(int lane) const {
+        uint4* p = reinterpret_cast<uint4*>(words);
+        const uint4 e = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+        for (uint32_t i = lane; i < (1u << tbits) / 8; i += 32) p[i] = e;
+        __syncwarp();
+    }
+    __device__ __forceinline__ bool insert(uint32_t id, bool* ovf) const {
+        const uint32_t bmask = (bbits >= 32) ? 0xFFFFFFFFu : ((1u << bbits) - 1u);
+        const uint32_t h = (id * 0x9E3779B1u) & bmask;
+        const uint32_t rbits = bbits - tbits;
+        const uint32_t home = h >> rbits;
+        const uint32_t rem16 = (h & ((1u << rbits) - 1u)) << 4;
+        const uint32_t tmask = (1u << tbits) - 1u;
+#pragma unroll 1
+        for (uint32_t d = 0; d < 15; ++d) {
+            const uint32_t slot = (home + d) & tmask;
+            const uint32_t mine = rem16 | d;
+            uint32_t* wp = words + (slot >> 1);
+            const uint32_t sh = (slot & 1u) * 16u;
+            uint32_t w = *reinterpret_cast<volatile uint32_t*>(wp);
+            while (true) {
+                uint32_t e = (w >> sh) & 0xFFFFu;
+                if (e == mine) return false;
+                if (e != 0xFFFFu) break;  // occupied by another id: next displacement
+                uint32_t old = atomicCAS(wp, w, (w & ~(0xFFFFu << sh)) | (mine << sh));
+                if (old == w) return true;
+                w = old;  // the word changed under us: re-examine
+            }
+        }
+        *ovf = true;
+        return true;
+    }
+};
+
+// ---------------------------------------------------------------------------
+// sorted key list in shared memory, lane-major access
+// ---------------------------------------------------------------------------
+// KPL > 0: compile-time keys per lane (capacity 32*KPL); KPL == 0: runtime kpl.
+template <int KPL>
+struct KeyList {
+    u64* list;
+    int kpl;  // keys per lane (even)
+    __device__ __forceinline__ int K() const { return KPL ? KPL : kpl; }
+    __device__ __forceinline__ int cap() const { return 32 * K(); }
+    __device__ __forceinline__ void reset(int lane) const {
+        for (int i = lane; i < cap(); i += 32) list[i] = SENTINEL;
+        __syncwarp();
+    }
+    // insert `key` (< list[ef-1] masked) keeping the list sorted and at most ef long.
+    // Returns the position.  All lanes call together.
+    __device__ __forceinline__ int insert(u64 key, int ef, int lane) const {
+        const int k = K();
+        const ulonglong2* p = reinterpret_cast<const ulonglong2*>(list + lane * k);
+        int c = 0;
+        if (KPL) {
+            u64 mine[KPL ? KPL : 2];
+#pragma unroll
+            for (int j = 0; j < KPL / 2; ++j) {
+                ulonglong2 v = p[j];
+                mine[2 * j] = v.x;
+                mine[2 * j + 1] = v.y;
+            }
+#pragma unroll
+            for (int j = 0; j < KPL; ++j) c += ((mine[j] & KEY_MASK) < key) ? 1 : 0;
+            const int full = __popc(__ballot_sync(HB_FULL, c == KPL));
+            const int cb = __shfl_sync(HB_FULL, c, full & 31);
+            const int pos = full * KPL + (full < 32 ? cb : 0);
+            __syncwarp();
+            // slot q >= pos moves to q + 1; the last slot of the array falls off
+#pragma unroll
+            for (int j = 0; j < KPL; ++j) {
+                const int q = lane * KPL + j;
+                if (q >= pos && q + 1 < 32 * KPL) list[q + 1] = mine[j];
+            }
+            __syncwarp();
+            if (lane == 0) {
+                list[pos] = key;
+                if (ef < 32 * KPL) list[ef] = SENTINEL;
+            }
+            __syncwarp();
+            return pos;
+        } else {
+            for (int j = 0; j < k / 2; ++j) {
+                ulonglong2 v = p[j];
+                c += ((v.x & KEY_MASK) < key) ? 1 : 0;
+                c += ((v.y & KEY_MASK) < key) ? 1 : 0;
+            }
+            const int full = __popc(__ballot_sync(HB_FULL, c == k));
+            const int cb = __shfl_sync(HB_FULL, c, full & 31);
+            const int pos = full * k + (full < 32 ? cb : 0);
+            // move from the top down, one 32-wide stripe at a time
+            const int last_src = min(ef, 32 * k) - 2;
+            for (int top = last_src; top >= pos; top -= 32) {
+                int j = top - lane;
+                bool mv = j >= pos;
+                u64 v = 0;
+                if (mv) v = list[j];
+                __syncwarp();
+                if (mv) list[j + 1] = v;
+                __syncwarp();
+            }
+            if (lane == 0) list[pos] = key;
+            __syncwarp();
+            return pos;
+        }
+    }
+};
+
+// helpers on a plain sorted array (used by the build's candidate window)
 __device__ __forceinline__ int list_lower_bound(const u64* list, int n, u64 key, int lane) {
     int lo = 0, len = n;
     while (len > 0) {
@@ -69,8 +216,6 @@ __device__ __forceinline__ int list_lower_bound(const u64* list, int n, u64 key,
     }
     return lo;
 }
-
-// insert key at pos, keeping at most ef entries (the last one is dropped when full)
 __device__ __forceinline__ void list_insert_at(u64* list, int& n, int ef, int pos, u64 key, int lane) {
     int last_src = (n < ef ? n : ef - 1) - 1;
     for (int top = last_src; top >= pos; top -= 32) {
@@ -87,69 +232,44 @@ __device__ __forceinline__ void list_insert_at(u64* list, int& n, int ef, int po
     __syncwarp();
 }
 
-__device__ __forceinline__ uint32_t vis_slot(uint32_t id, uint32_t shift) {
-    return (id * 0x9E3779B1u) >> shift;
-}
-
-// returns true if id was not yet in the set (and records it).  On a full probe
-// window the id is reported new but NOT recorded and *ovf is raised; the caller
-// then falls back to a list-membership test so results stay exact.
-__device__ __forceinline__ bool vis_insert(uint32_t* tab, uint32_t mask, uint32_t shift, uint32_t id,
-                                           bool* ovf) {
-    uint32_t h = vis_slot(id, shift);
-    for (int probe = 0; probe < 48; ++probe) {
-        uint32_t old = atomicCAS(&tab[h], EMPTY_ID, id);
-        if (old == EMPTY_ID) return true;
-        if (old == id) return false;
-        h = (h + 1) & mask;
-    }
-    *ovf = true;
-    return true;
-}
-
-__device__ __forceinline__ void vis_clear(uint32_t* tab, uint32_t slots, int lane) {
-    uint4* p = reinterpret_cast<uint4*>(tab);
-    const uint4 e = make_uint4(EMPTY_ID, EMPTY_ID, EMPTY_ID, EMPTY_ID);
-    for (uint32_t i = lane; i < slots / 4; i += 32) p[i] = e;
-    __syncwarp();
-}
-
-// One layer of best-first search.  On entry list[0..n) holds the entry set
-// (sorted, flags clear); on exit it holds the <= ef nearest evaluated nodes
-// (sorted, flags clear).  All 32 lanes execute this together.
-template <class Q>
+// ---------------------------------------------------------------------------
+// one layer of best-first search
+// ---------------------------------------------------------------------------
+// On entry the list holds the entry set (sorted, flags clear, sentinels behind it); on exit
+// it holds the <= ef nearest evaluated nodes (sorted, flags clear).  newbuf: 32 u32 scratch.
+template <class Q, class VIS, int KPL>
 __device__ __forceinline__ void search_layer(const Q& query, const uint8_t* __restrict__ rec,
                                              uint32_t rec_stride, const GraphView& g, uint32_t layer,
-                                             const WarpScratch& s, int& n, int ef, int lane,
-                                             SearchCounters& cnt) {
+                                             const KeyList<KPL>& L, const VIS& vis, uint32_t* newbuf,
+                                             int ef, int lane, SearchCounters& cnt) {
     const int gl = lane & 3, gbase = lane & ~3, grp = lane >> 2;
-    // upper layers see few nodes: use (and clear) only a slice of the table
-    const uint32_t slots = (layer == 0) ? s.vis_slots : min(s.vis_slots, 1024u);
-    const uint32_t vmask = slots - 1, vshift = 32 - (31 - __clz(slots));
-    vis_clear(s.vis, slots, lane);
-    // visited <- ids(selected)   (results.rs:159-168)
-    {
+    u64* list = L.list;
+    vis.clear(lane);
+    {   // visited <- ids(selected)   (results.rs:159-168)
         bool ovf = false;
-        for (int i = lane; i < n; i += 32) vis_insert(s.vis, vmask, vshift, (uint32_t)s.list[i], &ovf);
+        for (int i = lane; i < ef; i += 32) {
+            u64 k = list[i];
+            if (k != SENTINEL) vis.insert((uint32_t)k, &ovf);
+        }
         if (__any_sync(HB_FULL, ovf)) cnt.overflow = 1;
         __syncwarp();
     }
-    u64 worst = (n > 0) ? (s.list[n - 1] & KEY_MASK) : ~0ull;
-    int cursor = 0;  // every entry before `cursor` is expanded
+    u64 worst = list[ef - 1] & KEY_MASK;  // masked sentinel (max) while |selected| < ef
+    int cursor = 0;                       // every entry before `cursor` is expanded
     while (true) {
-        // candidates.pop_first(): first unexpanded entry
+        // candidates.pop_first(): first entry whose "expanded" bit is clear
         int found = -1;
-        for (int c = cursor; c < n; c += 32) {
+        for (int c = cursor; c < ef; c += 32) {
             int i = c + lane;
-            bool un = (i < n) && !(s.list[i] & EXP_FLAG);
+            bool un = (i < ef) && !(list[i] & EXP_FLAG);
             unsigned b = __ballot_sync(HB_FULL, un);
             if (b) { found = c + __ffs(b) - 1; break; }
         }
         if (found < 0) break;
         cursor = found;
-        const u64 ck = s.list[cursor];
+        const u64 ck = list[cursor];
         __syncwarp();
-        if (lane == 0) s.list[cursor] = ck | EXP_FLAG;
+        if (lane == 0) list[cursor] = ck | EXP_FLAG;
         __syncwarp();
         const uint32_t cid = (uint32_t)ck;
         cnt.hops++;
@@ -173,9 +293,9 @@ __device__ __forceinline__ void search_layer(const Q& query, const uint8_t* __re
                 cnt.nbrs += __popc(__ballot_sync(HB_FULL, valid));
                 // results.insert_visited(node)  (results.rs:101-103)
                 bool ovf = false;
-                bool isnew = valid && vis_insert(s.vis, vmask, vshift, nb, &ovf);
+                bool isnew = valid && vis.insert(nb, &ovf);
                 if (__any_sync(HB_FULL, ovf)) {
-                    // rare: table window full.  Exactness is kept by testing list membership.
+                    // rare: probe window exhausted.  Exactness is kept by testing list membership.
                     cnt.overflow = 1;
                     unsigned om = __ballot_sync(HB_FULL, ovf);
                     while (om) {
@@ -183,7 +303,10 @@ __device__ __forceinline__ void search_layer(const Q& query, const uint8_t* __re
                         om &= om - 1;
                         uint32_t id = __shfl_sync(HB_FULL, nb, src);
                         bool hit = false;
-                        for (int i2 = lane; i2 < n; i2 += 32) hit |= ((uint32_t)(s.list[i2] & ~EXP_FLAG) == id);
+                        for (int i2 = lane; i2 < ef; i2 += 32) {
+                            u64 k2 = list[i2];
+                            hit |= (k2 != SENTINEL) && ((uint32_t)(k2 & ~EXP_FLAG) == id);
+                        }
                         if (__any_sync(HB_FULL, hit) && lane == src) isnew = false;
                     }
                 }
@@ -191,27 +314,26 @@ __device__ __forceinline__ void search_layer(const Q& query, const uint8_t* __re
                 int ncnt = __popc(nm);
                 if (ncnt == 0) continue;
                 cnt.evals += ncnt;
-                if (isnew) s.newbuf[__popc(nm & ((1u << lane) - 1))] = nb;
+                if (isnew) newbuf[__popc(nm & ((1u << lane) - 1))] = nb;
                 __syncwarp();
                 for (int r0 = 0; r0 < ncnt; r0 += 8) {
                     int idx = r0 + grp;
                     bool act = idx < ncnt;
-                    uint32_t cand = s.newbuf[act ? idx : 0];
+                    uint32_t cand = newbuf[act ? idx : 0];
                     // index.get_point(node).dist2other(point)  (searcher.rs:66-69)
                     float d = query.dist(rec + (size_t)cand * rec_stride, gl, gbase);
                     u64 key = make_key(d, cand);
-                    // admission (searcher.rs:74-94): unconditional while |selected| < ef, else strict <
-                    bool want = act && gl == 0 && (n < ef || key < worst);
+                    // admission (searcher.rs:74-94): key < list[ef-1] covers |selected| < ef and strict <
+                    bool want = act && gl == 0 && key < worst;
                     unsigned am = __ballot_sync(HB_FULL, want);
                     while (am) {
                         int src = __ffs(am) - 1;
                         am &= am - 1;
                         u64 k = __shfl_sync(HB_FULL, key, src);
-                        if (n < ef || k < worst) {
-                            int pos = list_lower_bound(s.list, n, k, lane);
-                            list_insert_at(s.list, n, ef, pos, k, lane);
+                        if (k < worst) {
+                            int pos = L.insert(k, ef, lane);
                             minpos = min(minpos, pos);
-                            worst = (n >= ef) ? (s.list[n - 1] & KEY_MASK) : ~0ull;
+                            worst = list[ef - 1] & KEY_MASK;
                         }
                     }
                 }
@@ -222,8 +344,20 @@ __device__ __forceinline__ void search_layer(const Q& query, const uint8_t* __re
         cursor = min(cursor, minpos);
     }
     // clear_candidates (searcher.rs:100): drop the expanded marks for the next layer
-    for (int i = lane; i < n; i += 32) s.list[i] &= KEY_MASK;
+    for (int i = lane; i < ef; i += 32) {
+        u64 k = list[i];
+        if (k != SENTINEL) list[i] = k & KEY_MASK;
+    }
     __syncwarp();
+}
+
+// number of real entries among the first ef slots
+__device__ __forceinline__ int list_count(const u64* list, int ef, int lane) {
+    int c = 0;
+    for (int i = lane; i < ef; i += 32) c += (list[i] != SENTINEL) ? 1 : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(HB_FULL, c, o);
+    return c;
 }
 
 }  // namespace hb

@@ -200,45 +200,47 @@ def test_search_synthetic(H, oracle, dim, n, m, efc):
     check_search(H, oracle, orc, queries, 3, 50)
 
 
-def test_search_general_path_matches_fast_path(H, oracle, glove, glove_index, monkeypatch):
-    """ef <= 256 normally runs the register-list / 16-bit-visited kernel; the shared-memory-list kernel
-    (used for larger ef) must give the same answers and counters."""
+PATHS = [{}, {"HNSWB200_GENERAL_PATH": "1"}, {"HNSWB200_VIS32": "1"}, {"HNSWB200_GENERAL_PATH": "1", "HNSWB200_VIS32": "1"}]
+
+
+@pytest.mark.parametrize("env", PATHS)
+def test_search_kernel_variants_agree(H, oracle, glove, glove_index, monkeypatch, env):
+    """Template variants of the search kernel (fixed 4/8 keys per lane vs runtime list width; 16-bit vs
+    32-bit visited entries) must give the same answers and counters as the oracle."""
     _, queries = glove
     ix = to_gpu(H, glove_index)
-    fast = ix.ann_batch(queries, 10, 100, with_stats=True)
-    monkeypatch.setenv("HNSWB200_GENERAL_PATH", "1")
-    gen = ix.ann_batch(queries, 10, 100, with_stats=True)
-    monkeypatch.delenv("HNSWB200_GENERAL_PATH")
-    orc = glove_index.search_batch(queries, 10, 100)
-    for r in (fast, gen):
-        assert np.array_equal(r[0], orc[0]) and np.array_equal(bits(r[1]), bits(orc[1]))
-        assert np.array_equal(r[3]["hops"], orc[3]) and np.array_equal(r[3]["evals"], orc[4])
-    for ef in (64, 65, 128, 129, 256, 257):  # KPL boundaries of the register list
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    for ef in (1, 64, 100, 128, 129, 256, 257, 300):
         a = ix.ann_batch(queries, 10, ef, with_stats=True)
         o = glove_index.search_batch(queries, 10, ef)
-        assert np.array_equal(a[0], o[0]) and np.array_equal(bits(a[1]), bits(o[1]))
-        assert np.array_equal(a[3]["hops"], o[3]) and np.array_equal(a[3]["evals"], o[4])
-    for n in (1, 33, 100, 300):  # more results than list registers / than ef
+        assert np.array_equal(a[0], o[0]) and np.array_equal(bits(a[1]), bits(o[1])), ef
+        assert np.array_equal(a[3]["hops"], o[3]) and np.array_equal(a[3]["evals"], o[4]), ef
+    for n in (1, 33, 100, 300):  # more results than ef
         a = ix.ann_batch(queries[:20], n, 50)
         o = glove_index.search_batch(queries[:20], n, 50)
         assert np.array_equal(a[0], o[0]) and np.array_equal(a[2], o[2])
 
 
-@pytest.mark.parametrize("general", [False, True])
-def test_search_visited_overflow_both_paths(H, oracle, glove, glove_index, monkeypatch, general):
+@pytest.mark.parametrize("env", PATHS)
+def test_search_visited_overflow_all_paths(H, oracle, glove, glove_index, monkeypatch, env):
     _, queries = glove
     ix = to_gpu(H, glove_index)
     monkeypatch.setenv("HNSWB200_VIS_SLOTS", "64")
-    if general:
-        monkeypatch.setenv("HNSWB200_GENERAL_PATH", "1")
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
     ids, dists, counts, st = ix.ann_batch(queries, 10, 100, with_stats=True)
-    monkeypatch.delenv("HNSWB200_VIS_SLOTS")
-    if general:
-        monkeypatch.delenv("HNSWB200_GENERAL_PATH")
     oids, odists, ocounts, _, oevals = glove_index.search_batch(queries, 10, 100)
     assert (st["flags"] & 2).any()
     assert np.array_equal(ids, oids) and np.array_equal(bits(dists), bits(odists))
     assert (st["evals"] >= oevals).all()
+
+
+def test_build_with_32bit_visited(H, oracle, glove, glove_index, monkeypatch):
+    store, _ = glove
+    monkeypatch.setenv("HNSWB200_VIS32", "1")
+    ix = H.HNSW.new(12, None, 50).insert_bulk(store, batch=1)
+    assert_same_graph([ix.export_layer(l) for l in range(ix.nb_layers())], glove_index.export_layers())
 
 
 def test_search_visited_overflow_keeps_results_exact(H, oracle, glove, glove_index, monkeypatch):

@@ -37,14 +37,22 @@ def main():
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--oracle-sample", type=int, default=500)
     ap.add_argument("--efs", type=str, default="10,20,40,80,100,160,320")
+    ap.add_argument("--load", default="")
+    ap.add_argument("--save", default="")
     a = ap.parse_args()
     import torch
-    base = synth(a.n, a.dim, a.ncent, 1)
     queries = synth(a.nq, a.dim, a.ncent, 2)
     ctx = H.Context.default()
     t = time.time()
-    ix = H.HNSW.new(a.m, a.efc, a.dim).insert_bulk(base, batch=a.batch or None)
-    print(f"build: {time.time() - t:.2f}s  n={ix.len()} layers={ix.nb_layers()}", flush=True)
+    if a.load:
+        ix = H.HNSW.load(a.load)
+    else:
+        base = synth(a.n, a.dim, a.ncent, 1)
+        t = time.time()
+        ix = H.HNSW.new(a.m, a.efc, a.dim).insert_bulk(base, batch=a.batch or None)
+    print(f"build/load: {time.time() - t:.2f}s  n={ix.len()} layers={ix.nb_layers()}", flush=True)
+    if a.save:
+        ix.save(a.save)
     for l in range(ix.nb_layers()):
         ids, off, _ = ix.export_layer(l)
         deg = np.diff(off.astype(np.int64))
@@ -90,6 +98,7 @@ def main():
         for _ in range(3):
             ix.ann_batch(queries, 10, ef)
         e2e = (time.time() - t0) / 3
+        print(f"    evals max={evals.max()} p99={np.percentile(evals, 99):.0f} hops max={hops.max()} p99={np.percentile(hops, 99):.0f}")
         print(f"ef={ef:4d} recall={hits / (10 * nq):.4f} kernel={ms:8.3f} ms  qps={nq / ms * 1e3:12.0f}  e2e_qps={nq / e2e:12.0f} "
               f"hops={hops.mean():7.1f} evals={evals.mean():8.1f} nbrs={nbrs.mean():8.1f} ovf={ovf} "
               f"alg_GBps={bytes_alg / ms / 1e6:8.1f}", flush=True)
