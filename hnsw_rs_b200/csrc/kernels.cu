@@ -303,7 +303,7 @@ __device__ __forceinline__ void make_vis(Vis32& v, unsigned char* mem, const Sea
 }
 
 template <class Q, class VIS, int KPL>
-__global__ void __launch_bounds__(SEARCH_WPB * 32) search_kernel(SearchParams p) {
+__global__ void __launch_bounds__(SEARCH_WPB * 32, 5) search_kernel(SearchParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int gl = lane & 3, gbase = lane & ~3;
