@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhnsw_b200.so")
+LIB_PATH = os.environ.get("HNSWB200_LIB", os.path.join(_HERE, "libhnsw_b200.so"))  # env: A/B builds of the same ABI
 
 NO_ID = 0xFFFFFFFF
 

@@ -86,10 +86,23 @@ __device__ __forceinline__ float group_sum_sqrt(u64 acc, int gl, int gbase) {
 // Query held in registers, dimension known at compile time (dim = 8*NCH + REM).
 // All 32 lanes of the warp must call dist() together (it shuffles).
 // ---------------------------------------------------------------------------
+#ifndef HB_Q_SMEM
+#define HB_Q_SMEM 0  // 1: keep the dequantised query in shared memory instead of registers
+#endif
+
 template <int NCH, int REM>
 struct RegQuery {
     static constexpr int W = (int)hb_layout_W(NCH);
     static constexpr int TAIL = (int)hb_layout_tail(NCH, REM);
+#if HB_Q_SMEM
+    const float* qs;
+    __device__ __forceinline__ void init(const RecLayout&, const float* qd, int gl) { qs = qd + 2 * gl; }
+    __device__ __forceinline__ u64 qk(int k) const {
+        float2 v = *reinterpret_cast<const float2*>(qs + 8 * k);
+        return pk(v.x, v.y);
+    }
+    __device__ __forceinline__ float qrem(int r, int gl) const { return qs[8 * NCH + r - 2 * gl]; }
+#else
     u64 q[NCH ? NCH : 1];
     float qr[REM ? REM : 1];
 
@@ -103,6 +116,9 @@ struct RegQuery {
 #pragma unroll
         for (int r = 0; r < REM; ++r) qr[r] = qd[8 * NCH + r];
     }
+    __device__ __forceinline__ u64 qk(int k) const { return q[k]; }
+    __device__ __forceinline__ float qrem(int r, int) const { return qr[r]; }
+#endif
 
     __device__ __forceinline__ float dist(const uint8_t* __restrict__ rec, int gl, int gbase) const {
         const uint4* p = reinterpret_cast<const uint4*>(rec);
@@ -125,7 +141,7 @@ struct RegQuery {
 #pragma unroll
         for (int k = 0; k < NCH; ++k) {
             const int j = k / 8, c = k % 8;
-            acc = chunk_acc(acc, word32(w[j], c / 2), (c & 1) * 2, dl, mn2, q[k]);
+            acc = chunk_acc(acc, word32(w[j], c / 2), (c & 1) * 2, dl, mn2, qk(k));
         }
         if (REM > 0) {
             float a0, a1;
@@ -141,7 +157,7 @@ struct RegQuery {
                     const int pz = 2 * NCH + r, j = pz / 16, bi = pz % 16;
                     fm = magic_byte(word32(w[j], bi / 4), bi % 4);
                 }
-                n0 = rem_acc(n0, fm, dl, mn, qr[r]);
+                n0 = rem_acc(n0, fm, dl, mn, qrem(r, gl));
             }
             acc = pk(gl == 0 ? n0 : a0, a1);
         }

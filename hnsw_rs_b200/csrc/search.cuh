@@ -26,6 +26,19 @@
 #pragma once
 #include "dist.cuh"
 
+#ifndef HB_SPEC_ROW
+#define HB_SPEC_ROW 1      // load the adjacency row of the next-best unexpanded entry one hop ahead
+#endif
+#ifndef HB_SPEC_RECORDS
+#define HB_SPEC_RECORDS 1  // also prefetch the records of that row's unvisited neighbours
+#endif
+#ifndef HB_PREFETCH_BATCH
+#define HB_PREFETCH_BATCH 1  // request all new records of a batch before the first round
+#endif
+#ifndef HB_PREFETCH_OVERTAKE
+#define HB_PREFETCH_OVERTAKE 1  // prefetch the row of a new entry that overtakes the speculated one
+#endif
+
 namespace hb {
 
 constexpr uint32_t EMPTY_ID = 0xFFFFFFFFu;
@@ -293,7 +306,7 @@ __device__ __forceinline__ void search_layer(const Q& query, const uint8_t* __re
     // expanded, the adjacency row of the next-best unexpanded entry c2 is loaded and the records of
     // its not-yet-visited neighbours are prefetched into L2.  If c2 is indeed expanded next, its row
     // is already in registers and its records are (nearly) resident.
-    const bool speculate = (layer == 0) && (g.S0 <= 32);
+    const bool speculate = HB_SPEC_ROW && (layer == 0) && (g.S0 <= 32);
     u64 spec_key = SENTINEL;
     uint32_t spec_nb = EMPTY_ID;
     while (true) {
@@ -371,7 +384,7 @@ __device__ __forceinline__ void search_layer(const Q& query, const uint8_t* __re
                 }
                 // all records of this batch are requested at once (a second round does not pay
                 // a second memory latency)
-                if (isnew) {
+                if (HB_PREFETCH_BATCH && isnew) {
                     const uint8_t* rp8 = rec + (size_t)nb * rec_stride;
                     prefetch_l2(rp8);
                     if (rec_stride > 128) prefetch_l2(rp8 + 128);
@@ -388,7 +401,7 @@ __device__ __forceinline__ void search_layer(const Q& query, const uint8_t* __re
                     uint32_t cand = newbuf[act ? idx : 0];
                     // index.get_point(node).dist2other(point)  (searcher.rs:66-69)
                     float d = query.dist(rec + (size_t)cand * rec_stride, gl, gbase);
-                    if (!spec_prefetched) {
+                    if (HB_SPEC_RECORDS && !spec_prefetched) {
                         // the speculative row has arrived by now (it was requested before these records)
                         spec_prefetched = true;
                         bool sv = (nspec_nb != EMPTY_ID) && !(nspec_nb & CHAIN_BIT) && !vis.contains(nspec_nb);
@@ -411,7 +424,7 @@ __device__ __forceinline__ void search_layer(const Q& query, const uint8_t* __re
                             minpos = min(minpos, pos);
                             worst = list[ef - 1] & KEY_MASK;
                             // a new entry that overtakes c2 will be expanded first: fetch its row early
-                            if (speculate && lane == 0 && k < ck2) prefetch_l2(base + (size_t)(uint32_t)k * S);
+                            if (HB_PREFETCH_OVERTAKE && speculate && lane == 0 && k < ck2) prefetch_l2(base + (size_t)(uint32_t)k * S);
                         }
                     }
                 }
@@ -419,7 +432,7 @@ __device__ __forceinline__ void search_layer(const Q& query, const uint8_t* __re
             }
             row = next;
         }
-        if (!spec_prefetched) {
+        if (HB_SPEC_RECORDS && !spec_prefetched) {
             bool sv = (nspec_nb != EMPTY_ID) && !(nspec_nb & CHAIN_BIT) && !vis.contains(nspec_nb);
             if (sv) {
                 const uint8_t* sp8 = rec + (size_t)nspec_nb * rec_stride;
