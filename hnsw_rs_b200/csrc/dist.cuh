@@ -9,8 +9,18 @@
 // works on them as one packed f32x2 value (FADD2 on sm_100a).  Multiplications are
 // issued as scalar FMULs: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2
 // even with explicit rounding modifiers and --fmad=false, which would break the
-// contract; scalar mul.rn.f32 is never contracted (tools/check_sass.py verifies
-// that the built kernels contain no FFMA/FFMA2 in their distance loops).
+// contract; scalar mul.rn.f32 is never contracted.
+//
+// Fast path (RegQuery): the two multiplications are issued as packed FFMA2s that are
+// exact restatements of a single rounded product:
+//   rn(c * delta)  = fma(2^23 + c, delta, -(2^23 * delta))   the magic-number form of the u8
+//                    code enters directly; 2^23*delta is a power-of-two scaling (exact), the
+//                    fma forms (2^23+c)*delta - 2^23*delta = c*delta exactly and rounds once
+//   rn(t * t)      = fma(t, t, -0.0)                          adding -0 never changes a product
+// The -0.0 addend is read from constant memory so that ptxas cannot see it and turn the fma
+// back into a multiply it might then contract with the following add.  Records whose delta
+// is not below 2^100 (2^23*delta could overflow) take the scalar-multiply path.
+// tools/check_sass.py verifies the instruction mix; the GPU parity tests compare bit patterns.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -35,6 +45,13 @@ __device__ __forceinline__ u64 add2(u64 a, u64 b) {
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
     return r;
 }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+    u64 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+// pk(-0.0f, -0.0f); opaque to ptxas (see the header comment)
+static __constant__ u64 hb_negzero2 = 0x8000000080000000ull;
 __device__ __forceinline__ u64 sub2(u64 a, u64 b) {
     u64 r;
     asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
@@ -59,6 +76,13 @@ __device__ __forceinline__ u64 chunk_acc(u64 acc, uint32_t rr, int b0, float dl,
     float t0, t1;
     up(t, t0, t1);
     return add2(acc, pk(__fmul_rn(t0, t0), __fmul_rn(t1, t1)));
+}
+// fast form of chunk_acc: m2 = pk(2^23 + c0, 2^23 + c1); dl2 = pk(delta, delta);
+// nmd2 = pk(-(2^23*delta), ..); nz = pk(-0, -0)
+__device__ __forceinline__ u64 chunk_sq(u64 m2, u64 dl2, u64 nmd2, u64 mn2, u64 q, u64 nz) {
+    u64 x = add2(fma2(m2, dl2, nmd2), mn2);
+    u64 t = sub2(x, q);
+    return fma2(t, t, nz);
 }
 __device__ __forceinline__ float rem_acc(float a0, float fm, float dl, float mn, float q) {
     float c = __fadd_rn(fm, -8388608.0f);
@@ -86,25 +110,14 @@ __device__ __forceinline__ float group_sum_sqrt(u64 acc, int gl, int gbase) {
 // Query held in registers, dimension known at compile time (dim = 8*NCH + REM).
 // All 32 lanes of the warp must call dist() together (it shuffles).
 // ---------------------------------------------------------------------------
-#ifndef HB_Q_SMEM
-#define HB_Q_SMEM 0  // 1: keep the dequantised query in shared memory instead of registers
-#endif
-
 template <int NCH, int REM>
 struct RegQuery {
     static constexpr int W = (int)hb_layout_W(NCH);
     static constexpr int TAIL = (int)hb_layout_tail(NCH, REM);
-#if HB_Q_SMEM
-    const float* qs;
-    __device__ __forceinline__ void init(const RecLayout&, const float* qd, int gl) { qs = qd + 2 * gl; }
-    __device__ __forceinline__ u64 qk(int k) const {
-        float2 v = *reinterpret_cast<const float2*>(qs + 8 * k);
-        return pk(v.x, v.y);
-    }
-    __device__ __forceinline__ float qrem(int r, int gl) const { return qs[8 * NCH + r - 2 * gl]; }
-#else
+    static constexpr int RP = (REM + 1) / 2;  // remainder pairs
     u64 q[NCH ? NCH : 1];
-    float qr[REM ? REM : 1];
+    u64 qr[RP ? RP : 1];
+    u64 nz;
 
     // qd: dequantised query values in shared memory, natural element order
     __device__ __forceinline__ void init(const RecLayout&, const float* qd, int gl) {
@@ -114,11 +127,15 @@ struct RegQuery {
             q[k] = pk(v.x, v.y);
         }
 #pragma unroll
-        for (int r = 0; r < REM; ++r) qr[r] = qd[8 * NCH + r];
+        for (int r = 0; r < RP; ++r)
+            qr[r] = pk(qd[8 * NCH + 2 * r], (2 * r + 1 < REM) ? qd[8 * NCH + 2 * r + 1] : 0.0f);
+        nz = hb_negzero2;
     }
-    __device__ __forceinline__ u64 qk(int k) const { return q[k]; }
-    __device__ __forceinline__ float qrem(int r, int) const { return qr[r]; }
-#endif
+
+    // magic-number form (2^23 + code) of slice position pz of this lane
+    __device__ __forceinline__ static float slice_magic(const uint4 (&w)[W], int pz) {
+        return magic_byte(word32(w[pz / 16], (pz % 16) / 4), pz % 4);
+    }
 
     __device__ __forceinline__ float dist(const uint8_t* __restrict__ rec, int gl, int gbase) const {
         const uint4* p = reinterpret_cast<const uint4*>(rec);
@@ -138,26 +155,55 @@ struct RegQuery {
         }
         const u64 mn2 = pk(mn, mn);
         u64 acc = pk(0.0f, 0.0f);
+        if (__any_sync(HB_FULL, !(dl < 1.2676506e30f))) {
+            // delta >= 2^100, inf or NaN somewhere in this round: separately rounded multiplies
+#pragma unroll
+            for (int k = 0; k < NCH; ++k) {
+                const int j = k / 8, c = k % 8;
+                acc = chunk_acc(acc, word32(w[j], c / 2), (c & 1) * 2, dl, mn2, q[k]);
+            }
+            if (REM > 0) {
+                float a0, a1;
+                up(acc, a0, a1);
+                float n0 = a0;
+#pragma unroll
+                for (int r = 0; r < REM; ++r) {
+                    float fm = TAIL ? magic_byte(word32(tw, (8 + r) / 4), (8 + r) % 4) : slice_magic(w, 2 * NCH + r);
+                    float qa, qb;
+                    up(qr[r / 2], qa, qb);
+                    n0 = rem_acc(n0, fm, dl, mn, (r & 1) ? qb : qa);
+                }
+                acc = pk(gl == 0 ? n0 : a0, a1);
+            }
+            return group_sum_sqrt(acc, gl, gbase);
+        }
+        const u64 dl2 = pk(dl, dl);
+        const float nmd = __fmul_rn(-8388608.0f, dl);
+        const u64 nmd2 = pk(nmd, nmd);
 #pragma unroll
         for (int k = 0; k < NCH; ++k) {
-            const int j = k / 8, c = k % 8;
-            acc = chunk_acc(acc, word32(w[j], c / 2), (c & 1) * 2, dl, mn2, qk(k));
+            u64 m2 = pk(slice_magic(w, 2 * k), slice_magic(w, 2 * k + 1));
+            acc = add2(acc, chunk_sq(m2, dl2, nmd2, mn2, q[k], nz));
         }
         if (REM > 0) {
+            // remainder elements: squares in pairs, accumulated one by one into acc[0] (lane 0 of the group)
             float a0, a1;
             up(acc, a0, a1);
             float n0 = a0;
 #pragma unroll
-            for (int r = 0; r < REM; ++r) {
-                float fm;
+            for (int r = 0; r < RP; ++r) {
+                float f0, f1;
                 if (TAIL) {
-                    const int bi = 8 + r;
-                    fm = magic_byte(word32(tw, bi / 4), bi % 4);
+                    f0 = magic_byte(word32(tw, (8 + 2 * r) / 4), (8 + 2 * r) % 4);
+                    f1 = (2 * r + 1 < REM) ? magic_byte(word32(tw, (9 + 2 * r) / 4), (9 + 2 * r) % 4) : 8388608.0f;
                 } else {
-                    const int pz = 2 * NCH + r, j = pz / 16, bi = pz % 16;
-                    fm = magic_byte(word32(w[j], bi / 4), bi % 4);
+                    f0 = slice_magic(w, 2 * NCH + 2 * r);
+                    f1 = (2 * r + 1 < REM) ? slice_magic(w, 2 * NCH + 2 * r + 1) : 8388608.0f;
                 }
-                n0 = rem_acc(n0, fm, dl, mn, qrem(r, gl));
+                float s0, s1;
+                up(chunk_sq(pk(f0, f1), dl2, nmd2, mn2, qr[r], nz), s0, s1);
+                n0 = __fadd_rn(n0, s0);
+                if (2 * r + 1 < REM) n0 = __fadd_rn(n0, s1);
             }
             acc = pk(gl == 0 ? n0 : a0, a1);
         }

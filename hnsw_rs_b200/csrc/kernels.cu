@@ -13,6 +13,7 @@
 
 #include "kernels.h"
 #include "search.cuh"
+#include "search_reg.cuh"
 
 namespace hb {
 
@@ -372,6 +373,106 @@ __global__ void __launch_bounds__(SEARCH_WPB * 32, 5) search_kernel(SearchParams
     }
 }
 
+// The same query path on the register-resident list (ef <= 32*KPL): no shared-memory list, no
+// speculation; latency is hidden by warps (6 blocks of 4 warps per SM) instead.
+template <class VIS>
+__host__ __device__ inline size_t search_reg_warp_smem(uint32_t tbits, uint32_t qd_cap) {
+    return VIS::bytes(tbits) + 128 + (size_t)qd_cap * 4;
+}
+
+#ifndef HB_REG_MINB2
+#define HB_REG_MINB2 6  // resident blocks per SM the KPL=2 kernel is compiled for (register budget)
+#endif
+constexpr int reg_min_blocks(int kpl) { return kpl <= 2 ? HB_REG_MINB2 : kpl <= 4 ? 5 : 4; }
+
+template <class Q, class VIS, int KPL>
+__global__ void __launch_bounds__(SEARCH_WPB * 32, reg_min_blocks(KPL)) search_kernel_reg(SearchParams p) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int gl = lane & 3, gbase = lane & ~3;
+    unsigned char* wsm = smem + (size_t)wib * search_reg_warp_smem<VIS>(p.tbits, p.qd_cap);
+    VIS vis;
+    make_vis(vis, wsm, p);
+    uint32_t* newbuf = reinterpret_cast<uint32_t*>(wsm + VIS::bytes(p.tbits));
+    float* qd = reinterpret_cast<float*>(newbuf + 32);
+
+    while (true) {
+        uint32_t qi = 0;
+        if (lane == 0) qi = atomicAdd(p.work_counter, 1u);
+        qi = __shfl_sync(HB_FULL, qi, 0);
+        if (qi >= p.nq) break;
+        __syncwarp();
+        // Point::new(vector): the query is quantised exactly like a stored point (template.rs:313)
+        float mn, dl;
+        bool ok = warp_quantise(p.queries + (size_t)qi * p.L.dim, p.L.dim, lane, qd, nullptr, mn, dl);
+        __syncwarp();
+        uint32_t* oid = p.out_ids + (size_t)qi * p.topn;
+        float* od = p.out_dists ? p.out_dists + (size_t)qi * p.topn : nullptr;
+        if (!ok) {  // NaN in query: the reference panics; report through flags and an empty result
+            for (uint32_t j = lane; j < p.topn; j += 32) { oid[j] = EMPTY_ID; if (od) od[j] = INFINITY; }
+            if (lane == 0) {
+                if (p.out_counts) p.out_counts[qi] = 0;
+                if (p.out_hops) p.out_hops[qi] = 0;
+                if (p.out_evals) p.out_evals[qi] = 0;
+                if (p.out_flags) p.out_flags[qi] = 1u;
+                if (p.out_nbrs) p.out_nbrs[qi] = 0;
+            }
+            continue;
+        }
+        Q q;
+        q.init(p.L, qd, gl);
+        SearchCounters cnt{0u, 0u, 0u, 0u};
+        RegList<KPL> L;
+        search_query_reg<Q, VIS, KPL>(q, p.rec, p.L.stride, p.g, p.n_layers, p.ep, L, vis, newbuf, (int)p.ef, lane, cnt);
+        // get_top_selected(n)   (results.rs:59-61): position lane*KPL + s
+        uint32_t mine = 0;
+#pragma unroll
+        for (int s = 0; s < KPL; ++s) {
+            const uint32_t j = (uint32_t)(lane * KPL + s);
+            if (j < p.topn) {
+                const u64 k = L.v[s];
+                const bool real = (j < p.ef) && (k != RSENT);
+                oid[j] = real ? rkey_id(k) : EMPTY_ID;
+                if (od) od[j] = real ? __uint_as_float((uint32_t)(k >> 32)) : INFINITY;
+                mine += real ? 1u : 0u;
+            }
+        }
+        for (uint32_t j = 32 * KPL + lane; j < p.topn; j += 32) { oid[j] = EMPTY_ID; if (od) od[j] = INFINITY; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(HB_FULL, mine, o);
+        if (lane == 0) {
+            if (p.out_counts) p.out_counts[qi] = mine;
+            if (p.out_hops) p.out_hops[qi] = cnt.hops;
+            if (p.out_evals) p.out_evals[qi] = cnt.evals;
+            if (p.out_flags) p.out_flags[qi] = cnt.overflow ? 2u : 0u;
+            if (p.out_nbrs) p.out_nbrs[qi] = cnt.nbrs;
+        }
+    }
+}
+
+template <class Q, class VIS, int KPL>
+static cudaError_t launch_search_reg_t(const SearchParams& p, int num_sms, cudaStream_t st) {
+    size_t smem = search_reg_warp_smem<VIS>(p.tbits, p.qd_cap) * SEARCH_WPB;
+    if (smem > 227 * 1024) return cudaErrorInvalidValue;
+    static int occ_cache = 0;
+    static size_t occ_smem = 0;
+    cudaError_t e;
+    if (occ_cache == 0 || occ_smem != smem) {
+        e = cudaFuncSetAttribute(search_kernel_reg<Q, VIS, KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        int occ = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, search_kernel_reg<Q, VIS, KPL>, SEARCH_WPB * 32, smem);
+        if (e != cudaSuccess) return e;
+        occ_cache = occ < 1 ? 1 : occ;
+        occ_smem = smem;
+    }
+    uint64_t want = ((uint64_t)p.nq + SEARCH_WPB - 1) / SEARCH_WPB;
+    uint64_t cap = (uint64_t)num_sms * occ_cache;
+    int grid = (int)(want < cap ? want : cap);
+    search_kernel_reg<Q, VIS, KPL><<<grid, SEARCH_WPB * 32, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
 template <class Q, class VIS, int KPL>
 static cudaError_t launch_search_t(const SearchParams& p, int num_sms, cudaStream_t st) {
     size_t smem = search_warp_smem<VIS>(p.kpl, p.tbits, p.qd_cap) * SEARCH_WPB;
@@ -435,7 +536,28 @@ cudaError_t launch_search(const SearchLaunch& a, int num_sms, cudaStream_t st) {
     bool use16;
     choose_visited(a.ef, a.g.S0, a.n_points, &p.tbits, &p.bbits, &use16);
     const bool generic_list = a.ef > 256 || getenv("HNSWB200_GENERAL_PATH");
+    const bool smem_list = generic_list || getenv("HNSWB200_SMEM_LIST");  // test knobs: force the older paths
     p.kpl = generic_list ? round_up((a.ef + 31) / 32, 2) : (a.ef <= 128 ? 4 : 8);
+    if (!smem_list) {
+        // register-resident list: ef <= 64 / 128 / 256 -> 2 / 4 / 8 keys per lane
+        auto rbytes = [&](uint32_t tb) {
+            return (use16 ? search_reg_warp_smem<Vis16>(tb, p.qd_cap) : search_reg_warp_smem<Vis32>(tb, p.qd_cap)) * SEARCH_WPB;
+        };
+        while (rbytes(p.tbits) > 200 * 1024 && p.tbits > 9 && (!use16 || p.bbits <= p.tbits - 1 + 12)) --p.tbits;
+        cudaError_t e0 = cudaMemsetAsync(a.work_counter, 0, sizeof(uint32_t), st);
+        if (e0 != cudaSuccess) return e0;
+        HB_DISPATCH_DIM(a.L, {
+            if (use16) {
+                if (a.ef <= 64) return launch_search_reg_t<Q, Vis16, 2>(p, num_sms, st);
+                if (a.ef <= 128) return launch_search_reg_t<Q, Vis16, 4>(p, num_sms, st);
+                return launch_search_reg_t<Q, Vis16, 8>(p, num_sms, st);
+            }
+            if (a.ef <= 64) return launch_search_reg_t<Q, Vis32, 2>(p, num_sms, st);
+            if (a.ef <= 128) return launch_search_reg_t<Q, Vis32, 4>(p, num_sms, st);
+            return launch_search_reg_t<Q, Vis32, 8>(p, num_sms, st);
+        });
+        return cudaErrorUnknown;
+    }
     // shrink the visited table if one block would not fit (the overflow fallback keeps results exact)
     auto bytes = [&](uint32_t tb) {
         return (use16 ? search_warp_smem<Vis16>(p.kpl, tb, p.qd_cap) : search_warp_smem<Vis32>(p.kpl, tb, p.qd_cap)) * SEARCH_WPB;

@@ -96,6 +96,27 @@ struct Vis32 {
         *ovf = true;
         return true;
     }
+    // warp-uniform form of insert (see Vis16::insert_warp)
+    __device__ __forceinline__ bool insert_warp(uint32_t id, bool want, bool* ovf) const {
+        const uint32_t mask = (1u << tbits) - 1u;
+        uint32_t h = (id * 0x9E3779B1u) >> (32 - tbits);
+        bool pending = want, isnew = false;
+        int probes = 0;
+#pragma unroll 1
+        while (__any_sync(HB_FULL, pending)) {
+            uint32_t old = id;
+            if (pending) old = atomicCAS(&tab[h], EMPTY_ID, id);
+            const bool won = pending && old == EMPTY_ID;
+            const bool step = pending && old != EMPTY_ID && old != id;
+            h = step ? ((h + 1) & mask) : h;
+            probes += step ? 1 : 0;
+            const bool full = step && probes >= 48;
+            if (full) *ovf = true;
+            isnew = isnew || won || full;
+            pending = step && !full;
+        }
+        return isnew;
+    }
     // read-only membership test (used to filter speculative prefetches; "unknown" counts as absent)
     __device__ __forceinline__ bool contains(uint32_t id) const {
         const uint32_t mask = (1u << tbits) - 1u;
@@ -150,6 +171,38 @@ struct Vis16 {
         }
         *ovf = true;
         return true;
+    }
+    // The same insertion for all 32 lanes at once with warp-uniform control flow (want: this lane has
+    // an id to record).  Every lane executes every iteration of the one loop, so the warp never
+    // splits into separately scheduled fragments.  Returns "id was new" per lane.
+    __device__ __forceinline__ bool insert_warp(uint32_t id, bool want, bool* ovf) const {
+        const uint32_t bmask = (bbits >= 32) ? 0xFFFFFFFFu : ((1u << bbits) - 1u);
+        const uint32_t h = (id * 0x9E3779B1u) & bmask;
+        const uint32_t rbits = bbits - tbits;
+        const uint32_t rem16 = (h & ((1u << rbits) - 1u)) << 4;
+        const uint32_t tmask = (1u << tbits) - 1u;
+        uint32_t slot = h >> rbits, mine = rem16;  // mine = rem16 | displacement
+        bool pending = want, isnew = false;
+#pragma unroll 1
+        while (__any_sync(HB_FULL, pending)) {
+            uint32_t* wp = words + (slot >> 1);
+            const uint32_t sh = (slot & 1u) * 16u;
+            const uint32_t w = *reinterpret_cast<volatile uint32_t*>(wp);
+            const uint32_t e = (w >> sh) & 0xFFFFu;
+            const bool hit = pending && e == mine;
+            const bool free_ = pending && e == 0xFFFFu;
+            bool won = false;
+            if (free_) won = atomicCAS(wp, w, (w & ~(0xFFFFu << sh)) | (mine << sh)) == w;
+            // occupied by another id: next displacement; a lost race re-examines the same slot
+            const bool step = pending && !hit && !free_;
+            slot = step ? ((slot + 1) & tmask) : slot;
+            mine += step ? 1u : 0u;
+            const bool full = step && (mine & 15u) == 15u;
+            if (full) *ovf = true;
+            isnew = isnew || won || full;
+            pending = pending && !hit && !won && !full;
+        }
+        return isnew;
     }
     __device__ __forceinline__ bool contains(uint32_t id) const {
         const uint32_t bmask = (bbits >= 32) ? 0xFFFFFFFFu : ((1u << bbits) - 1u);

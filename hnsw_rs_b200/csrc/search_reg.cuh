@@ -1,0 +1,222 @@
+// HNSW::ann_by_vector on a register-resident result list (ef <= 32*KPL), one warp per query.
+//
+// Same algorithm and the same results, counters included, as search_layer in search.cuh
+// (Searcher::search_layer, hnsw/src/template/searcher.rs:23-103, driven by HNSW::ann_by_vector,
+// hnsw/src/template.rs:306-335).  What differs is the shape of the code: the kernel is bound by
+// instruction issue and by the instruction cache (24 warps per SM, each at its own program
+// counter), so the whole query -- entry point, greedy upper layers, layer 0 -- runs through ONE
+// loop with one instance each of the visited-set insert, the distance evaluation and the list
+// insertion.  One iteration handles one batch of up to 32 neighbour ids:
+//   boot batch   the entry point alone (selected <- {Dist(ep, d)}, template.rs:316-319)
+//   seed batch   the surviving entry of the layer above, recorded as visited but not evaluated
+//                (results.rs:148-168 at the start of every search_layer)
+//   row batch    32 slots of the adjacency row of the popped candidate
+//
+// Key layout: (f32 bits of dist << 32) | (id << 1) | expanded.  ids are < 2^31, so id << 1 fits;
+// keys of different ids compare like Dist::cmp (graph/src/dist.rs:30-37) whatever their flag bits,
+// and a new key (flag clear) is never < an entry with the same (dist, id).  Position p of the
+// sorted list lives in lane p / KPL, slot p % KPL: an insertion moves keys inside a lane by
+// register renaming and hands one key to the next lane with a single shuffle.
+#pragma once
+#include "search.cuh"
+
+namespace hb {
+
+constexpr u64 RSENT = ~0ull;
+
+__device__ __forceinline__ u64 make_rkey(float d, uint32_t id) {
+    return ((u64)__float_as_uint(d) << 32) | (u64)(id << 1);
+}
+__device__ __forceinline__ uint32_t rkey_id(u64 k) { return (uint32_t)k >> 1; }
+__device__ __forceinline__ u64 sel64(bool c, u64 a, u64 b) { return c ? a : b; }
+
+template <int KPL>
+struct RegList {
+    u64 v[KPL];
+
+    __device__ __forceinline__ void reset() {
+#pragma unroll
+        for (int s = 0; s < KPL; ++s) v[s] = RSENT;
+    }
+    // key at position p (warp-uniform), broadcast to all lanes
+    __device__ __forceinline__ u64 get(int p) const {
+        const int s = p % KPL;
+        u64 x = v[0];
+#pragma unroll
+        for (int t = 1; t < KPL; ++t) x = sel64(s == t, v[t], x);
+        return __shfl_sync(HB_FULL, x, p / KPL);
+    }
+    // Insert `key` (same value in all lanes, < the key at position ef-1) keeping the list sorted;
+    // the key at position ef (lane == ef_lane, slot ef_slot) is dropped.
+    __device__ __forceinline__ void insert(u64 key, int lane, int ef_lane, int ef_slot) {
+        int c = 0;
+#pragma unroll
+        for (int s = 0; s < KPL; ++s) c += (v[s] < key) ? 1 : 0;
+        const int l0 = __popc(__ballot_sync(HB_FULL, c == KPL));  // lanes before l0 hold smaller keys only
+        const u64 inc = __shfl_up_sync(HB_FULL, v[KPL - 1], 1);
+        // lanes after l0 move every slot up (slot 0 takes the previous lane's last key); lane l0
+        // moves the slots above c and puts the key into slot c; lanes before l0 keep their keys
+        c = lane > l0 ? -1 : (lane == l0 ? c : KPL);
+        const int ts = lane == ef_lane ? ef_slot : -1;
+#pragma unroll
+        for (int s = KPL - 1; s >= 0; --s) {
+            u64 nv = sel64(s > c, s ? v[s ? s - 1 : 0] : inc, v[s]);
+            nv = sel64(s == c, key, nv);
+            v[s] = sel64(s == ts, RSENT, nv);
+        }
+    }
+    // candidates.pop_first(): the first entry whose "expanded" bit is clear; marks it expanded.
+    // Returns false when there is none.
+    __device__ __forceinline__ bool pop(u64& ck, int lane) {
+        int fs = -1;
+        u64 mine = RSENT;
+#pragma unroll
+        for (int s = KPL - 1; s >= 0; --s) {
+            const bool un = !((uint32_t)v[s] & 1u);
+            fs = un ? s : fs;
+            mine = sel64(un, v[s], mine);
+        }
+        const unsigned m = __ballot_sync(HB_FULL, fs >= 0);
+        if (!m) return false;
+        const int l = __ffs(m) - 1;
+        ck = __shfl_sync(HB_FULL, mine, l);
+        fs = lane == l ? fs : -1;
+#pragma unroll
+        for (int s = 0; s < KPL; ++s) v[s] |= (s == fs) ? 1ull : 0ull;
+        return true;
+    }
+    __device__ __forceinline__ void clear_flags() {  // clear_candidates (searcher.rs:100)
+#pragma unroll
+        for (int s = 0; s < KPL; ++s) v[s] = sel64(v[s] != RSENT, v[s] & ~1ull, v[s]);
+    }
+    __device__ __forceinline__ bool holds_id(uint32_t id) const {
+        bool hit = false;
+#pragma unroll
+        for (int s = 0; s < KPL; ++s) hit |= (v[s] != RSENT) && (rkey_id(v[s]) == id);
+        return __any_sync(HB_FULL, hit);
+    }
+};
+
+// One whole query.  On exit L holds the <= ef nearest evaluated nodes of layer 0, sorted.
+// Layers n_layers-1 .. 1 are searched with ef = 1 (template.rs:322-324), layer 0 with ef (:326).
+template <class Q, class VIS, int KPL>
+__device__ __forceinline__ void search_query_reg(const Q& query, const uint8_t* __restrict__ rec,
+                                                 uint32_t rec_stride, const GraphView& g, uint32_t n_layers,
+                                                 uint32_t ep, RegList<KPL>& L, const VIS& vis,
+                                                 uint32_t* newbuf, int ef, int lane, SearchCounters& cnt) {
+    const int gl = lane & 3, gbase = lane & ~3, grp = lane >> 2;
+    uint32_t layer = n_layers - 1;
+    int ef_l = layer ? 1 : ef;
+    int ef_lane = ef_l < 32 * KPL ? ef_l / KPL : -1, ef_slot = ef_l % KPL;
+    L.reset();
+    u64 worst = RSENT;  // key at position ef_l - 1: the sentinel (max) while |selected| < ef_l
+    vis.clear(lane);
+    // boot batch: the entry point
+    uint32_t nb = lane == 0 ? ep : EMPTY_ID;
+    bool seed = false;
+    uint32_t row = EMPTY_ID, next = EMPTY_ID, b0 = 0;
+#pragma unroll 1
+    while (true) {
+        // Independent thread scheduling keeps a warp split once its lanes have left a divergent region
+        // by different exits; every collective below would then run once per fragment.  The explicit
+        // barriers re-join the warp at the top of each batch and after the per-lane hash probing.
+        __syncwarp();
+        // ---- one batch of up to 32 ids: results.insert_visited(node) (results.rs:101-103) ----
+        const bool valid = !(nb & CHAIN_BIT);  // EMPTY_ID and chain markers carry bit 31
+        bool ovf = false;
+        bool isnew = vis.insert_warp(nb, valid, &ovf);
+        if (__any_sync(HB_FULL, ovf)) {
+            // rare: probe window exhausted.  Exactness is kept by testing list membership.
+            cnt.overflow = 1;
+            unsigned om = __ballot_sync(HB_FULL, ovf);
+#pragma unroll 1
+            while (om) {
+                const int src = __ffs(om) - 1;
+                om &= om - 1;
+                const uint32_t id = __shfl_sync(HB_FULL, nb, src);
+                if (L.holds_id(id) && lane == src) isnew = false;
+            }
+        }
+        isnew = isnew && !seed;
+        const unsigned nm = __ballot_sync(HB_FULL, isnew);
+        const int ncnt = __popc(nm);
+        if (ncnt) {
+            cnt.evals += ncnt;
+            if (isnew) {
+                const int my = __popc(nm & ((1u << lane) - 1));
+                newbuf[my] = nb;
+                // records of the second and later rounds are requested now, so that those rounds
+                // do not pay a second memory latency
+                if (my >= 8) {
+                    const uint8_t* rp8 = rec + (size_t)nb * rec_stride;
+                    prefetch_l2(rp8);
+                    if (rec_stride > 128) prefetch_l2(rp8 + 128);
+                }
+            }
+            __syncwarp();
+#pragma unroll 1
+            for (int r0 = 0; r0 < ncnt; r0 += 8) {
+                const int idx = r0 + grp;
+                const bool act = idx < ncnt;
+                const uint32_t cand = newbuf[act ? idx : 0];
+                // index.get_point(node).dist2other(point)  (searcher.rs:66-69)
+                const float d = query.dist(rec + (size_t)cand * rec_stride, gl, gbase);
+                const u64 key = make_rkey(d, cand);
+                // admission (searcher.rs:74-94): key < list[ef-1] covers |selected| < ef and strict <
+                unsigned am = __ballot_sync(HB_FULL, act && gl == 0 && key < worst);
+#pragma unroll 1
+                while (am) {
+                    const int src = __ffs(am) - 1;
+                    am &= am - 1;
+                    const u64 k = __shfl_sync(HB_FULL, key, src);
+                    if (k < worst) {
+                        L.insert(k, lane, ef_lane, ef_slot);
+                        worst = L.get(ef_l - 1);
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        // ---- next batch ----
+        if (row != EMPTY_ID) {  // more of the current adjacency row (rows wider than 32, continuation rows)
+            b0 += 32;
+            if (b0 >= (layer ? g.SU : g.S0)) { row = next; next = EMPTY_ID; b0 = 0; }
+        }
+        seed = false;
+        if (row == EMPTY_ID) {
+            u64 ck;
+            if (!L.pop(ck, lane)) {
+                // this layer is finished: selected survives as the entry set of the next one
+                L.clear_flags();
+                if (layer == 0) break;
+                --layer;
+                ef_l = layer ? 1 : ef;
+                ef_lane = ef_l < 32 * KPL ? ef_l / KPL : -1;
+                ef_slot = ef_l % KPL;
+                worst = L.get(ef_l - 1);
+                vis.clear(lane);
+                // seed batch: visited <- ids(selected); the upper layers ran with ef = 1, so the
+                // entry set is the single key at position 0
+                nb = (lane == 0 && L.v[0] != RSENT) ? rkey_id(L.v[0]) : EMPTY_ID;
+                seed = true;
+                continue;
+            }
+            cnt.hops++;
+            // layer.neighbors_vec(cid)  (graph/src/graph.rs:103-113) as fixed-stride rows
+            const uint32_t cid = rkey_id(ck);
+            row = layer ? __ldg(g.upper_off + cid) + (layer - 1) : cid;
+        }
+        {
+            const uint32_t S = layer ? g.SU : g.S0;
+            const uint32_t* rp = (layer ? g.upper_adj : g.adj0) + (size_t)row * S;
+            const uint32_t i = b0 + lane;
+            nb = (i < S) ? __ldg(rp + i) : EMPTY_ID;
+            const bool ok = !(nb & CHAIN_BIT);
+            const unsigned mk = __ballot_sync(HB_FULL, !ok && nb != EMPTY_ID);
+            if (mk) next = __shfl_sync(HB_FULL, nb, __ffs(mk) - 1) & ~CHAIN_BIT;
+            cnt.nbrs += __popc(__ballot_sync(HB_FULL, ok));
+        }
+    }
+}
+
+}  // namespace hb
