@@ -321,7 +321,9 @@ def main():
         traffic = json.load(open(os.path.join(ROOT, "profiles", "search_kernel_traffic.json"))).get("dram_bytes_per_launch")
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "hb::search_kernel<RegQuery<12,4>,Vis16,4>", "achieved": round(achieved, 1),
+    kname = ("hb::search_kernel_reg<RegQuery<12,4>,Vis16,%d>" % (2 if ef <= 64 else 4 if ef <= 128 else 8)) if ef <= 256 \
+        else "hb::search_kernel<RegQuery<12,4>,Vis16,0>"
+    roofline = {"bound": "hbm", "kernel": kname, "achieved": round(achieved, 1),
                 "peak": peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                 "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
                 "algorithmic_bytes_per_launch": ab, "kernel_ms": round(kern_ms, 4),

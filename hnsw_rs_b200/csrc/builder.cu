@@ -117,7 +117,10 @@ __device__ __forceinline__ bool heuristic_fill(const Q& query, const uint8_t* __
     }
     {
         bool ovf = false;
-        for (int i = lane; i < n; i += 32) vis.insert((uint32_t)(list[i] & KEY_MASK), &ovf);
+        for (int i0 = 0; i0 < n; i0 += 32) {
+            const int i = i0 + lane;
+            vis.insert_warp(i < n ? (uint32_t)(list[i] & KEY_MASK) : 0u, i < n, &ovf);
+        }
         __syncwarp();
     }
     for (int si = 0; si < n; ++si) {
@@ -141,7 +144,7 @@ __device__ __forceinline__ bool heuristic_fill(const Q& query, const uint8_t* __
                 // table window is full the id is simply evaluated again (duplicate keys are
                 // skipped by the consumer).
                 bool ovf = false;
-                bool isnew = valid && vis.insert(nb, &ovf);
+                bool isnew = vis.insert_warp(nb, valid, &ovf);
                 unsigned nm = __ballot_sync(HB_FULL, isnew);
                 int ncnt = __popc(nm);
                 if (ncnt == 0) continue;

@@ -500,8 +500,9 @@ static cudaError_t launch_search_t(const SearchParams& p, int num_sms, cudaStrea
 void choose_visited(uint32_t ef, uint32_t S0, uint64_t n_points, uint32_t* tbits, uint32_t* bbits, bool* use16) {
     uint32_t bb = 1;
     while (bb < 31 && (1ull << bb) < n_points) ++bb;
-    // observed: evaluations per query ~ 0.35 * ef * S0; aim at a load factor around 0.25
-    uint64_t want = (uint64_t)ef * (S0 ? S0 : 32) * 3 / 2;
+    // observed on the C2 workload (S0 = 32): ~390 evaluations per query at ef = 10, ~830 at ef = 64,
+    // ~980 at ef = 100 (p99 about 1.7x the mean); aim at a mean load factor around 0.25
+    uint64_t want = (uint64_t)ef * (S0 ? S0 : 32) * 3 / 4 + 1024;
     uint32_t tb = 9;
     while ((1ull << tb) < want && tb < 16) ++tb;
     if (const char* ev = getenv("HNSWB200_VIS_SLOTS")) {  // test knob: force the overflow fallback
@@ -535,10 +536,9 @@ cudaError_t launch_search(const SearchLaunch& a, int num_sms, cudaStream_t st) {
     p.work_counter = a.work_counter;
     bool use16;
     choose_visited(a.ef, a.g.S0, a.n_points, &p.tbits, &p.bbits, &use16);
-    const bool generic_list = a.ef > 256 || getenv("HNSWB200_GENERAL_PATH");
-    const bool smem_list = generic_list || getenv("HNSWB200_SMEM_LIST");  // test knobs: force the older paths
-    p.kpl = generic_list ? round_up((a.ef + 31) / 32, 2) : (a.ef <= 128 ? 4 : 8);
-    if (!smem_list) {
+    const bool generic_list = a.ef > 256 || getenv("HNSWB200_GENERAL_PATH");  // env: test knob
+    p.kpl = round_up((a.ef + 31) / 32, 2);
+    if (!generic_list) {
         // register-resident list: ef <= 64 / 128 / 256 -> 2 / 4 / 8 keys per lane
         auto rbytes = [&](uint32_t tb) {
             return (use16 ? search_reg_warp_smem<Vis16>(tb, p.qd_cap) : search_reg_warp_smem<Vis32>(tb, p.qd_cap)) * SEARCH_WPB;
@@ -565,12 +565,9 @@ cudaError_t launch_search(const SearchLaunch& a, int num_sms, cudaStream_t st) {
     while (bytes(p.tbits) > 200 * 1024 && p.tbits > 9 && (!use16 || p.bbits <= p.tbits - 1 + 12)) --p.tbits;
     cudaError_t e = cudaMemsetAsync(a.work_counter, 0, sizeof(uint32_t), st);
     if (e != cudaSuccess) return e;
+    // ef > 256: sorted list in shared memory, runtime width
     HB_DISPATCH_DIM(a.L, {
-        if (use16) {
-            if (generic_list) return launch_search_t<Q, Vis16, 0>(p, num_sms, st);
-            if (p.kpl == 4) return launch_search_t<Q, Vis16, 4>(p, num_sms, st);
-            return launch_search_t<Q, Vis16, 8>(p, num_sms, st);
-        }
+        if (use16) return launch_search_t<Q, Vis16, 0>(p, num_sms, st);
         return launch_search_t<Q, Vis32, 0>(p, num_sms, st);
     });
     return cudaErrorUnknown;

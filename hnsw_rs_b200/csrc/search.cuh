@@ -346,9 +346,10 @@ __device__ __forceinline__ void search_layer(const Q& query, const uint8_t* __re
     vis.clear(lane);
     {   // visited <- ids(selected)   (results.rs:159-168)
         bool ovf = false;
-        for (int i = lane; i < ef; i += 32) {
-            u64 k = list[i];
-            if (k != SENTINEL) vis.insert((uint32_t)k, &ovf);
+        for (int i0 = 0; i0 < ef; i0 += 32) {
+            const int i = i0 + lane;
+            const u64 k = i < ef ? list[i] : SENTINEL;
+            vis.insert_warp((uint32_t)k, k != SENTINEL, &ovf);
         }
         if (__any_sync(HB_FULL, ovf)) cnt.overflow = 1;
         __syncwarp();
@@ -418,7 +419,7 @@ __device__ __forceinline__ void search_layer(const Q& query, const uint8_t* __re
                 cnt.nbrs += __popc(__ballot_sync(HB_FULL, valid));
                 // results.insert_visited(node)  (results.rs:101-103)
                 bool ovf = false;
-                bool isnew = valid && vis.insert(nb, &ovf);
+                bool isnew = vis.insert_warp(nb, valid, &ovf);
                 if (__any_sync(HB_FULL, ovf)) {
                     // rare: probe window exhausted.  Exactness is kept by testing list membership.
                     cnt.overflow = 1;

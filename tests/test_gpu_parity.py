@@ -205,8 +205,9 @@ PATHS = [{}, {"HNSWB200_GENERAL_PATH": "1"}, {"HNSWB200_VIS32": "1"}, {"HNSWB200
 
 @pytest.mark.parametrize("env", PATHS)
 def test_search_kernel_variants_agree(H, oracle, glove, glove_index, monkeypatch, env):
-    """Template variants of the search kernel (fixed 4/8 keys per lane vs runtime list width; 16-bit vs
-    32-bit visited entries) must give the same answers and counters as the oracle."""
+    """Variants of the search kernel (register-resident list with 2/4/8 keys per lane vs the shared-memory
+    list of runtime width; 16-bit vs 32-bit visited entries) must give the same answers and counters as
+    the oracle."""
     _, queries = glove
     ix = to_gpu(H, glove_index)
     for k, v in env.items():

@@ -119,6 +119,14 @@ def main():
             tn = time.time() - t0
             ok = (np.array_equal(ids, oids) and np.array_equal(dists.view(np.uint32), od.view(np.uint32))
                   and np.array_equal(st["hops"], oh) and np.array_equal(st["evals"], oe))
+            if not ok:
+                fl = st["flags"] if "flags" in st else None
+                bad_ids = np.flatnonzero((ids != oids).any(axis=1))
+                bad_h = np.flatnonzero(st["hops"] != oh)
+                bad_e = np.flatnonzero(st["evals"] != oe)
+                print(f"   mismatch detail: ids rows={len(bad_ids)} dists={int((dists.view(np.uint32) != od.view(np.uint32)).sum())} "
+                      f"hops rows={len(bad_h)} evals rows={len(bad_e)} "
+                      f"overflow-flagged among evals-mismatch={int((fl[bad_e] & 2 != 0).sum()) if fl is not None else 'n/a'}")
             print(f"oracle parity ef={ef}: {'OK' if ok else 'MISMATCH'}  cpu qps 1thr={len(qs) / t1:.0f} {os.cpu_count()}thr={len(qs) / tn:.0f}",
                   flush=True)
 
