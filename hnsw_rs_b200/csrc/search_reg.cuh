@@ -20,6 +20,10 @@
 #pragma once
 #include "search.cuh"
 
+#ifndef HB_PREFETCH_ROWS
+#define HB_PREFETCH_ROWS 0  // prefetch the layer-0 adjacency row of every key admitted to the list
+#endif
+
 namespace hb {
 
 constexpr u64 RSENT = ~0ull;
@@ -117,10 +121,6 @@ __device__ __forceinline__ void search_query_reg(const Q& query, const uint8_t* 
     uint32_t row = EMPTY_ID, next = EMPTY_ID, b0 = 0;
 #pragma unroll 1
     while (true) {
-        // Independent thread scheduling keeps a warp split once its lanes have left a divergent region
-        // by different exits; every collective below would then run once per fragment.  The explicit
-        // barriers re-join the warp at the top of each batch and after the per-lane hash probing.
-        __syncwarp();
         // ---- one batch of up to 32 ids: results.insert_visited(node) (results.rs:101-103) ----
         const bool valid = !(nb & CHAIN_BIT);  // EMPTY_ID and chain markers carry bit 31
         bool ovf = false;
@@ -172,6 +172,9 @@ __device__ __forceinline__ void search_query_reg(const Q& query, const uint8_t* 
                     if (k < worst) {
                         L.insert(k, lane, ef_lane, ef_slot);
                         worst = L.get(ef_l - 1);
+                        // every node that is ever expanded was admitted first: request its adjacency row
+                        // now, so that the pop finds it in L2
+                        if (HB_PREFETCH_ROWS && layer == 0 && lane == 0) prefetch_l2(g.adj0 + (size_t)rkey_id(k) * g.S0);
                     }
                 }
             }
