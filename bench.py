@@ -12,7 +12,8 @@ value  = queries/s with the queries already resident in HBM (CUDA events, max ov
 e2e    = the same through the host-buffer entry point hnswb200_search (pinned host queries in,
          ids / distances / counts out), host<->device copies inside the timed region.
 N > 1: the index is replicated, every rank searches its own 10,000 queries (weak scaling), and
-the ids are all-gathered over NCCL inside the timed region so that every rank holds all results.
+the ids are all-gathered over NCCL inside the timed region so that every rank holds all results
+(the gather of step s runs on NCCL's stream while step s+1 searches; two result buffers).
 """
 import argparse
 import ctypes as C
@@ -166,6 +167,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: hnsw_rs_b200 has no CPU fallback "
                          "(the reference arm also builds its index with the device builder)")
     torch.cuda.set_device(local_rank)
+    os.environ["NCCL_DEBUG"] = os.environ.get("HNSWB200_NCCL_DEBUG", "WARN")  # keep NCCL's banner off stdout: ONE JSON line
     if world > 1 and a.impl == "b200":
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -204,9 +206,9 @@ def main():
     d_nb = torch.empty(nq, dtype=torch.int32, device="cuda")
     lib = _ffi.lib()
 
-    def search_dev(ef):
-        _ffi.check(lib.hnswb200_search_dev(ctx.h, ix.h, dq.data_ptr(), nq, K, ef, d_ids.data_ptr(), d_d.data_ptr(),
-                                           d_cnt.data_ptr(), d_h.data_ptr(), d_e.data_ptr(), d_f.data_ptr(),
+    def search_dev(ef, ids=None):
+        _ffi.check(lib.hnswb200_search_dev(ctx.h, ix.h, dq.data_ptr(), nq, K, ef, (ids if ids is not None else d_ids).data_ptr(),
+                                           d_d.data_ptr(), d_cnt.data_ptr(), d_h.data_ptr(), d_e.data_ptr(), d_f.data_ptr(),
                                            d_nb.data_ptr()))
 
     def search_ids(ef):
@@ -240,8 +242,11 @@ def main():
         search_dev(ef)
     torch.cuda.synchronize()
     if world > 1:
-        gathered = torch.empty((world, nq, K), dtype=torch.int32, device="cuda")
-        dist.all_gather_into_tensor(gathered, d_ids)
+        # the ids of step s are all-gathered (NCCL, its own stream) while step s+1 searches: two result buffers
+        ids2 = [d_ids, torch.empty_like(d_ids)]
+        gathered = [torch.empty((world * nq, K), dtype=torch.int32, device="cuda") for _ in range(2)]
+        pending = [None, None]
+        dist.all_gather_into_tensor(gathered[0], d_ids)
         dist.barrier()
     torch.cuda.synchronize()
     sampler = ClockSampler(local_rank)
@@ -251,11 +256,18 @@ def main():
     k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
     e0.record()
     for s in range(a.steps):
+        b = s & 1
+        if world > 1 and pending[b] is not None:
+            pending[b].wait()  # the buffer pair of step s-2 is free again
         k_ev[s][0].record()
-        search_dev(ef)
+        search_dev(ef, ids2[b] if world > 1 else None)
         k_ev[s][1].record()
         if world > 1:
-            dist.all_gather_into_tensor(gathered, d_ids)
+            pending[b] = dist.all_gather_into_tensor(gathered[b], ids2[b], async_op=True)
+    if world > 1:
+        for h in pending:
+            if h is not None:
+                h.wait()
     e1.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -336,6 +348,8 @@ def main():
                 "steps": a.steps, "warmup": a.warmup, "ms_per_step": total_ms / a.steps, "config": cfg, "e2e": e2e,
                 "roofline": roofline, "clocks": clocks, "note": "profiling helper run, no cpu_baseline"}
         print(json.dumps(line), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
         return 0
     orc = oracle_from_index(ix)
     cores = os.cpu_count() or 1

@@ -5,6 +5,7 @@
 #include <errno.h>
 #include <math.h>
 #include <stdio.h>
+#include <time.h>
 #include <stdlib.h>
 #include <string.h>
 #include <sys/stat.h>
@@ -36,6 +37,15 @@ int hnswb200_ctx::ws_reserve(size_t bytes) {
     cudaError_t e = cudaMalloc(&d_ws, want);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(workspace)");
     ws_bytes = want;
+    return 0;
+}
+
+int hnswb200_ctx::bf_ws_reserve(size_t bytes) {
+    if (bytes <= bf_ws_bytes) return 0;
+    if (d_bf_ws) { cudaStreamSynchronize(stream); cudaFree(d_bf_ws); d_bf_ws = nullptr; bf_ws_bytes = 0; }
+    cudaError_t e = cudaMalloc(&d_bf_ws, bytes);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(brute-force workspace)");
+    bf_ws_bytes = bytes;
     return 0;
 }
 
@@ -81,6 +91,7 @@ void hnswb200_ctx_destroy(hnswb200_ctx* c) {
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     if (c->d_scratch) cudaFree(c->d_scratch);
     if (c->d_ws) cudaFree(c->d_ws);
+    if (c->d_bf_ws) cudaFree(c->d_bf_ws);
     delete c;
 }
 
@@ -784,14 +795,27 @@ int hnswb200_bruteforce_topk_dev(hnswb200_ctx* c, const hnswb200_points* base, c
     if (c->use()) return HNSWB200_ECUDA;
     const RecLayout& L = base->L;
     const uint32_t cap = 2048;
-    DevBuf<uint8_t> qrec;
-    DevBuf<uint64_t> topk, tau, buf;
-    DevBuf<uint32_t> cnt;
-    HB_CUDA(qrec.alloc(nq * L.stride));
-    HB_CUDA(topk.alloc(nq * k));
-    HB_CUDA(tau.alloc(nq));
-    HB_CUDA(buf.alloc(nq * cap));
-    HB_CUDA(cnt.alloc(nq));
+    const uint64_t N = base->n, MAXCH = 1ull << 18;
+    // Tensor-core filter (bf_tc.cu) for every chunk after the first: the first (exact) chunk establishes
+    // the thresholds.  HNSWB200_BF_NO_TC forces the CUDA-core path (test knob).
+    const bool use_tc = bf_tc_supported(L) && N > 2 * cap && !getenv("HNSWB200_BF_NO_TC");
+    const uint64_t nq_pad = (nq + 127) / 128 * 128;
+    // all scratch comes from one grow-only workspace
+    struct Carve {
+        unsigned char* base = nullptr;
+        size_t off = 0;
+        size_t take(size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; }
+    } cv;
+    const size_t o_qrec = cv.take(nq * L.stride), o_topk = cv.take(nq * k * 8), o_tau = cv.take(nq * 8),
+                 o_buf = cv.take(nq * (size_t)cap * 8), o_cnt = cv.take(nq * 4),
+                 o_bconst = cv.take(use_tc ? N * 16 : 0), o_qstat = cv.take(use_tc ? nq * 16 : 0),
+                 o_qconst = cv.take(use_tc ? nq_pad * 16 : 0), o_amask = cv.take(use_tc ? nq_pad * 128 : 0);
+    if (c->bf_ws_reserve(cv.off)) return HNSWB200_ECUDA;
+    unsigned char* W = (unsigned char*)c->d_bf_ws;
+    struct { uint8_t* p; } qrec{W + o_qrec}, amask{W + o_amask};
+    struct { uint64_t* p; } topk{(uint64_t*)(W + o_topk)}, tau{(uint64_t*)(W + o_tau)}, buf{(uint64_t*)(W + o_buf)};
+    struct { uint32_t* p; } cnt{(uint32_t*)(W + o_cnt)};
+    struct { float4* p; } bconst{(float4*)(W + o_bconst)}, qstat{(float4*)(W + o_qstat)}, qconst{(float4*)(W + o_qconst)};
     uint32_t* nan_flag = c->d_scratch + 1;
     uint32_t* ovf_flag = c->d_scratch + 2;
     HB_CUDA(cudaMemsetAsync(nan_flag, 0, 8, c->stream));
@@ -808,15 +832,36 @@ int hnswb200_bruteforce_topk_dev(hnswb200_ctx* c, const hnswb200_points* base, c
     // Chunks double in size: with tau = current k-th best, the expected number of survivors of a
     // chunk as large as everything seen before is <= k per query.  A chunk that overflows the
     // per-query buffer (adversarial order) is redone in pieces of `cap` rows, which cannot overflow.
-    const uint64_t N = base->n, MAXCH = 1ull << 18;
+    if (use_tc) {
+        HB_CUDA(cudaMemsetAsync(amask.p, 0, nq_pad * 128, c->stream));
+        HB_CUDA(bf_tc_prepare(base->d_rec, N, L, qrec.p, (uint32_t)nq, bconst.p, amask.p, qstat.p, c->stream));
+    }
     uint64_t done = 0;
     while (done < N) {
-        uint64_t ch = done == 0 ? std::min<uint64_t>(cap, N) : std::min<uint64_t>(std::min<uint64_t>(done, MAXCH), N - done);
-        HB_CUDA(launch_bf_chunk(base->d_rec, L, done, done + ch, id_offset, qrec.p, (uint32_t)nq, tau.p, buf.p,
-                                cap, cnt.p, ovf_flag, c->stream));
+        // first chunk: enough rows for a useful k-th distance, few enough for a cheap merge
+        uint64_t first = 256;
+        while (first < 4ull * k && first < cap) first <<= 1;
+        uint64_t ch = done == 0 ? std::min<uint64_t>(use_tc ? first : cap, N) : std::min<uint64_t>(std::min<uint64_t>(done, MAXCH), N - done);
+        if (use_tc && done > 0)
+            HB_CUDA(bf_tc_chunk(base->d_rec, N, L, done, done + ch, id_offset, qrec.p, amask.p, qstat.p, bconst.p, qconst.p,
+                                (uint32_t)nq, reinterpret_cast<const unsigned long long*>(tau.p),
+                                reinterpret_cast<unsigned long long*>(buf.p), cap, cnt.p, ovf_flag, c->num_sms, c->stream));
+        else
+            HB_CUDA(launch_bf_chunk(base->d_rec, L, done, done + ch, id_offset, qrec.p, (uint32_t)nq, tau.p, buf.p,
+                                    cap, cnt.p, ovf_flag, c->stream));
         uint32_t ovf = 0;
         HB_CUDA(cudaMemcpyAsync(&ovf, ovf_flag, 4, cudaMemcpyDeviceToHost, c->stream));
         HB_CUDA(cudaStreamSynchronize(c->stream));
+        if (getenv("HNSWB200_BF_PROFILE")) {
+            static double t_prev = 0;
+            timespec ts;
+            clock_gettime(CLOCK_MONOTONIC, &ts);
+            double t_now = ts.tv_sec + ts.tv_nsec * 1e-9;
+            fprintf(stderr, "[hnswb200 bruteforce] rows [%llu, %llu) %s overflow=%u  +%.2f ms\n", (unsigned long long)done,
+                    (unsigned long long)(done + ch), (use_tc && done > 0) ? "tensor-core filter" : "exact", ovf,
+                    (t_now - t_prev) * 1e3);
+            t_prev = t_now;
+        }
         if (ovf) {
             HB_CUDA(cudaMemsetAsync(ovf_flag, 0, 4, c->stream));
             HB_CUDA(cudaMemsetAsync(cnt.p, 0, nq * 4, c->stream));
@@ -842,11 +887,10 @@ int hnswb200_bruteforce_topk(hnswb200_ctx* c, const hnswb200_points* base, const
     if (!c || !base || (nq && (!queries || !out_ids))) return fail(HNSWB200_EINVAL, "bruteforce: NULL argument");
     if (nq == 0) return 0;
     if (c->use()) return HNSWB200_ECUDA;
-    DevBuf<float> dq, dd;
-    DevBuf<uint32_t> dids;
-    HB_CUDA(dq.alloc(nq * base->L.dim));
-    HB_CUDA(dids.alloc(nq * k));
-    HB_CUDA(dd.alloc(nq * k));
+    const size_t qb = (nq * base->L.dim * 4 + 255) & ~(size_t)255, ib = ((size_t)nq * k * 4 + 255) & ~(size_t)255;
+    if (c->ws_reserve(qb + 2 * ib)) return HNSWB200_ECUDA;
+    struct { float* p; } dq{(float*)c->d_ws}, dd{(float*)((unsigned char*)c->d_ws + qb + ib)};
+    struct { uint32_t* p; } dids{(uint32_t*)((unsigned char*)c->d_ws + qb)};
     HB_CUDA(cudaMemcpyAsync(dq.p, queries, nq * base->L.dim * 4, cudaMemcpyHostToDevice, c->stream));
     int rc = hnswb200_bruteforce_topk_dev(c, base, dq.p, nq, k, id_offset, dids.p, dd.p);
     if (rc) return rc;

@@ -36,6 +36,9 @@ struct hnswb200_ctx {
     uint32_t* d_scratch = nullptr;  // [0] work counter, [1] nan flag, [2] overflow flag, ...
     void* d_ws = nullptr;           // grow-only workspace for the host-buffer entry points
     size_t ws_bytes = 0;
+    void* d_bf_ws = nullptr;        // grow-only scratch of the brute-force entry points (cudaMalloc per call costs more than the kernels)
+    size_t bf_ws_bytes = 0;
+    int bf_ws_reserve(size_t bytes);
     std::vector<uint32_t> h_flags;
     int ws_reserve(size_t bytes);
     int use() const;                // cudaSetDevice

@@ -639,6 +639,10 @@ __global__ void __launch_bounds__(256) bf_merge_kernel(uint64_t* topk, uint32_t 
     uint64_t* a = reinterpret_cast<uint64_t*>(smem);
     const uint32_t qi = blockIdx.x;
     uint32_t m = min(cnt[qi], cap);
+    // sort only as wide as this query needs (P is the allocation: next_pow2(k + cap))
+    uint32_t Pq = 1;
+    while (Pq < k + m) Pq <<= 1;
+    P = Pq;
     for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) {
         uint64_t v = ~0ull;
         if (i < k) v = topk[(size_t)qi * k + i];

@@ -70,6 +70,16 @@ cudaError_t launch_bf_merge(uint64_t* topk, uint32_t k, uint64_t* tau, uint64_t*
                             uint32_t* cnt, uint32_t nq, cudaStream_t st);
 cudaError_t launch_keys_to_out(const uint64_t* topk, uint32_t k, uint32_t nq, uint32_t* ids,
                                float* dists, cudaStream_t st);
+// brute force on the tensor cores (bf_tc.cu): tcgen05 kind::i8 contraction of the code bytes as a filter,
+// exact re-rank of the survivors.  Only for records of exactly 128 bytes (dim 96 / 100).
+bool bf_tc_supported(const RecLayout& L);
+cudaError_t bf_tc_prepare(const uint8_t* base_rec, uint64_t n, const RecLayout& L, const uint8_t* qrec, uint32_t nq,
+                          float4* bconst, uint8_t* amask, float4* qstat, cudaStream_t st);
+cudaError_t bf_tc_chunk(const uint8_t* base_rec, uint64_t n_base, const RecLayout& L, uint64_t row0, uint64_t row_end,
+                        uint32_t id_offset, const uint8_t* qrec, const uint8_t* amask, const float4* qstat,
+                        const float4* bconst, float4* qconst, uint32_t nq, const unsigned long long* tau,
+                        unsigned long long* cand, uint32_t cap, uint32_t* cnt, uint32_t* overflow, int num_sms,
+                        cudaStream_t st);
 // merge G sorted lists of k (ids/dists [G][nq][k]) into one list of k per query
 cudaError_t launch_topk_merge(const uint32_t* ids, const float* dists, uint32_t G, uint32_t nq,
                               uint32_t k, uint32_t* out_ids, float* out_dists, cudaStream_t st);
