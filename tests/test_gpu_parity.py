@@ -315,6 +315,67 @@ def test_bruteforce_adversarial_order(H, oracle):
     assert np.array_equal(ids, oids) and np.array_equal(bits(dists), bits(odists))
 
 
+def _flat_oracle(oracle, base, dim):
+    n = len(base)
+    codes, mins, deltas = oracle.quantise_rows(base)
+    return oracle.Index.from_parts(4, 8, dim, 0, codes, mins, deltas, np.zeros(n, np.uint8),
+                                   [(np.arange(n, dtype=np.uint32), np.zeros(n + 1, np.uint64), np.zeros(0, np.uint32))])
+
+
+@pytest.mark.parametrize("dim", [100, 96])
+def test_bruteforce_tensor_core_adversarial_order(H, oracle, dim, monkeypatch):
+    """The tcgen05 filter path (records of 128 bytes) with the base sorted by decreasing distance: candidate lists
+    overflow, the chunk is redone by the exact kernel; and the same data through the CUDA-core path."""
+    n = 30000
+    r = np.random.default_rng(3)
+    base = r.standard_normal((n, dim)).astype(np.float32) * 0.05
+    base[:, 0] += np.linspace(10.0, 1.0, n, dtype=np.float32)
+    q = r.standard_normal((5, dim)).astype(np.float32) * 0.05
+    orc = _flat_oracle(oracle, base, dim)
+    oids, odists = orc.bruteforce(q, 10, threads=8)
+    pts = H.SimplePoints.new(base)
+    ids, dists = H.bruteforce_topk(pts, q, 10)
+    assert np.array_equal(ids, oids) and np.array_equal(bits(dists), bits(odists))
+    monkeypatch.setenv("HNSWB200_BF_NO_TC", "1")
+    ids, dists = H.bruteforce_topk(pts, q, 10)
+    assert np.array_equal(ids, oids) and np.array_equal(bits(dists), bits(odists))
+
+
+def test_bruteforce_tensor_core_extreme_records(H, oracle):
+    """Records the algebraic filter cannot rank (constant vectors: delta = 0; huge offsets; huge ranges; exact
+    duplicates) must still come out exactly: the filter only ever lets too many through, never too few."""
+    dim, n = 100, 20000
+    r = np.random.default_rng(11)
+    base = r.standard_normal((n, dim)).astype(np.float32)
+    base[100] = 0.25                      # constant vector: delta = 0, every code 0 (quant.rs:154-166)
+    base[101] = base[7]                   # exact duplicate: tie broken by id
+    base[200:300] += np.float32(1.0e4)    # large offset: cancellation in Sum x^2 + Sum y^2 - 2 Sum xy
+    base[300:400] *= np.float32(1.0e3)    # large range
+    base[400:420] *= np.float32(1.0e-6)   # tiny range around zero
+    q = np.concatenate([base[[7, 100, 250, 350, 410]], r.standard_normal((27, dim)).astype(np.float32)])
+    q[6] += np.float32(1.0e4)
+    orc = _flat_oracle(oracle, base, dim)
+    for k in (1, 10, 100):
+        oids, odists = orc.bruteforce(q, k, threads=8)
+        ids, dists = H.bruteforce_topk(H.SimplePoints.new(base), q, k)
+        assert np.array_equal(ids, oids), k
+        assert np.array_equal(bits(dists), bits(odists)), k
+
+
+def test_bruteforce_tensor_core_large_matches_cuda_core_path(H, monkeypatch):
+    """Size-independent property at a scale the oracle does not reach in seconds: both device paths agree bit for bit
+    (300,000 x 100 base, 2,000 queries, top-100), results are sorted by (dist, id) and ids are unique per query."""
+    base = synth(300000, 100, 512, 21)
+    q = synth(2000, 100, 512, 22)
+    pts = H.SimplePoints.new(base)
+    ids, dists = H.bruteforce_topk(pts, q, 100)
+    monkeypatch.setenv("HNSWB200_BF_NO_TC", "1")
+    ids2, dists2 = H.bruteforce_topk(pts, q, 100)
+    assert np.array_equal(ids, ids2) and np.array_equal(bits(dists), bits(dists2))
+    key = (bits(dists).astype(np.uint64) << np.uint64(32)) | ids.astype(np.uint64)
+    assert (np.diff(key.astype(np.int64), axis=1) > 0).all()
+
+
 # ---- save / load (hnsw/src/template.rs:43-131, 574-611) ---------------------------------------------
 def test_save_load_cross_with_oracle(H, oracle, glove, glove_index, tmp_path):
     _, queries = glove
