@@ -81,6 +81,8 @@ int hnswb200_ctx_create(int device, hnswb200_ctx** out) {
     c->own_stream = true;
     HB_CUDA(cudaMalloc((void**)&c->d_scratch, 64 * sizeof(uint32_t)));
     HB_CUDA(cudaMemset(c->d_scratch, 0, 64 * sizeof(uint32_t)));
+    HB_CUDA(cudaMalloc((void**)&c->d_counters, hnswb200_ctx::COUNTER_RING * sizeof(uint32_t)));
+    HB_CUDA(cudaMemset(c->d_counters, 0, hnswb200_ctx::COUNTER_RING * sizeof(uint32_t)));
     *out = c;
     return 0;
 }
@@ -90,6 +92,7 @@ void hnswb200_ctx_destroy(hnswb200_ctx* c) {
     cudaSetDevice(c->device);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     if (c->d_scratch) cudaFree(c->d_scratch);
+    if (c->d_counters) cudaFree(c->d_counters);
     if (c->d_ws) cudaFree(c->d_ws);
     if (c->d_bf_ws) cudaFree(c->d_bf_ws);
     delete c;
@@ -733,7 +736,13 @@ int hnswb200_search_dev(hnswb200_ctx* c, const hnswb200_index* ix, const float* 
     a.out_evals = d_evals;
     a.out_flags = d_flags;
     a.out_nbrs = d_nbrs;
-    a.work_counter = c->d_scratch;
+    // counter ring (engine.h): slot 0 follows a memset of the whole ring and is an ordinary launch; the other
+    // slots are launched as programmatic dependents of whatever kernel precedes them in the stream
+    const uint32_t slot = (uint32_t)(c->search_seq++ % hnswb200_ctx::COUNTER_RING);
+    if (slot == 0) HB_CUDA(cudaMemsetAsync(c->d_counters, 0, hnswb200_ctx::COUNTER_RING * sizeof(uint32_t), c->stream));
+    a.work_counter = c->d_counters + slot;
+    a.counter_is_fresh = true;
+    a.overlap_previous = slot != 0 && !getenv("HNSWB200_NO_PDL");
     HB_CUDA(launch_search(a, c->num_sms, c->stream));
     return 0;
 }

@@ -33,7 +33,13 @@ struct hnswb200_ctx {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     int num_sms = 148;
-    uint32_t* d_scratch = nullptr;  // [0] work counter, [1] nan flag, [2] overflow flag, ...
+    uint32_t* d_scratch = nullptr;  // [0] work counter (build), [1] nan flag, [2] overflow flag, ...
+    // Work counters of the search launches: a ring of zeroed slots, one per launch, re-zeroed by ONE memset each
+    // time the ring wraps.  No memset sits between two consecutive searches, so a search may be launched as the
+    // programmatic dependent of the previous one and fill the SMs its tail leaves idle (hnswb200_search_dev).
+    static constexpr uint32_t COUNTER_RING = 32;
+    uint32_t* d_counters = nullptr;
+    uint64_t search_seq = 0;
     void* d_ws = nullptr;           // grow-only workspace for the host-buffer entry points
     size_t ws_bytes = 0;
     void* d_bf_ws = nullptr;        // grow-only scratch of the brute-force entry points (cudaMalloc per call costs more than the kernels)

@@ -395,6 +395,9 @@ __global__ void __launch_bounds__(SEARCH_WPB * 32, reg_min_blocks(KPL)) search_k
     make_vis(vis, wsm, p);
     uint32_t* newbuf = reinterpret_cast<uint32_t*>(wsm + VIS::bytes(p.tbits));
     float* qd = reinterpret_cast<float*>(newbuf + 32);
+    // A following search (launched as programmatic dependent) reads nothing this grid writes: let its blocks
+    // take over the SMs as soon as this grid's blocks retire, instead of waiting for the last long query.
+    asm volatile("griddepcontrol.launch_dependents;");
 
     while (true) {
         uint32_t qi = 0;
@@ -451,7 +454,7 @@ __global__ void __launch_bounds__(SEARCH_WPB * 32, reg_min_blocks(KPL)) search_k
 }
 
 template <class Q, class VIS, int KPL>
-static cudaError_t launch_search_reg_t(const SearchParams& p, int num_sms, cudaStream_t st) {
+static cudaError_t launch_search_reg_t(const SearchParams& p, int num_sms, cudaStream_t st, bool overlap_previous) {
     size_t smem = search_reg_warp_smem<VIS>(p.tbits, p.qd_cap) * SEARCH_WPB;
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
     static int occ_cache = 0;
@@ -469,8 +472,17 @@ static cudaError_t launch_search_reg_t(const SearchParams& p, int num_sms, cudaS
     uint64_t want = ((uint64_t)p.nq + SEARCH_WPB - 1) / SEARCH_WPB;
     uint64_t cap = (uint64_t)num_sms * occ_cache;
     int grid = (int)(want < cap ? want : cap);
-    search_kernel_reg<Q, VIS, KPL><<<grid, SEARCH_WPB * 32, smem, st>>>(p);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(SEARCH_WPB * 32);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = overlap_previous ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, search_kernel_reg<Q, VIS, KPL>, p);
 }
 
 template <class Q, class VIS, int KPL>
@@ -544,17 +556,19 @@ cudaError_t launch_search(const SearchLaunch& a, int num_sms, cudaStream_t st) {
             return (use16 ? search_reg_warp_smem<Vis16>(tb, p.qd_cap) : search_reg_warp_smem<Vis32>(tb, p.qd_cap)) * SEARCH_WPB;
         };
         while (rbytes(p.tbits) > 200 * 1024 && p.tbits > 9 && (!use16 || p.bbits <= p.tbits - 1 + 12)) --p.tbits;
-        cudaError_t e0 = cudaMemsetAsync(a.work_counter, 0, sizeof(uint32_t), st);
-        if (e0 != cudaSuccess) return e0;
+        if (!a.counter_is_fresh) {
+            cudaError_t e0 = cudaMemsetAsync(a.work_counter, 0, sizeof(uint32_t), st);
+            if (e0 != cudaSuccess) return e0;
+        }
         HB_DISPATCH_DIM(a.L, {
             if (use16) {
-                if (a.ef <= 64) return launch_search_reg_t<Q, Vis16, 2>(p, num_sms, st);
-                if (a.ef <= 128) return launch_search_reg_t<Q, Vis16, 4>(p, num_sms, st);
-                return launch_search_reg_t<Q, Vis16, 8>(p, num_sms, st);
+                if (a.ef <= 64) return launch_search_reg_t<Q, Vis16, 2>(p, num_sms, st, a.overlap_previous);
+                if (a.ef <= 128) return launch_search_reg_t<Q, Vis16, 4>(p, num_sms, st, a.overlap_previous);
+                return launch_search_reg_t<Q, Vis16, 8>(p, num_sms, st, a.overlap_previous);
             }
-            if (a.ef <= 64) return launch_search_reg_t<Q, Vis32, 2>(p, num_sms, st);
-            if (a.ef <= 128) return launch_search_reg_t<Q, Vis32, 4>(p, num_sms, st);
-            return launch_search_reg_t<Q, Vis32, 8>(p, num_sms, st);
+            if (a.ef <= 64) return launch_search_reg_t<Q, Vis32, 2>(p, num_sms, st, a.overlap_previous);
+            if (a.ef <= 128) return launch_search_reg_t<Q, Vis32, 4>(p, num_sms, st, a.overlap_previous);
+            return launch_search_reg_t<Q, Vis32, 8>(p, num_sms, st, a.overlap_previous);
         });
         return cudaErrorUnknown;
     }
@@ -563,8 +577,10 @@ cudaError_t launch_search(const SearchLaunch& a, int num_sms, cudaStream_t st) {
         return (use16 ? search_warp_smem<Vis16>(p.kpl, tb, p.qd_cap) : search_warp_smem<Vis32>(p.kpl, tb, p.qd_cap)) * SEARCH_WPB;
     };
     while (bytes(p.tbits) > 200 * 1024 && p.tbits > 9 && (!use16 || p.bbits <= p.tbits - 1 + 12)) --p.tbits;
-    cudaError_t e = cudaMemsetAsync(a.work_counter, 0, sizeof(uint32_t), st);
-    if (e != cudaSuccess) return e;
+    if (!a.counter_is_fresh) {
+        cudaError_t e = cudaMemsetAsync(a.work_counter, 0, sizeof(uint32_t), st);
+        if (e != cudaSuccess) return e;
+    }
     // ef > 256: sorted list in shared memory, runtime width
     HB_DISPATCH_DIM(a.L, {
         if (use16) return launch_search_t<Q, Vis16, 0>(p, num_sms, st);
