@@ -29,7 +29,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-EF_SWEEP = [10, 20, 40, 48, 56, 64, 72, 80, 100, 160, 320, 640]  # BASELINE's sweep plus steps between 40 and 80
+EF_SWEEP = [10, 20, 40, 48, 52, 56, 57, 58, 59, 60, 62, 64, 72, 80, 100, 160, 320, 640]  # BASELINE's sweep, refined between 40 and 80
 K = 10
 
 

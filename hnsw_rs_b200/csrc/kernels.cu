@@ -470,7 +470,12 @@ static cudaError_t launch_search_reg_t(const SearchParams& p, int num_sms, cudaS
         occ_smem = smem;
     }
     uint64_t want = ((uint64_t)p.nq + SEARCH_WPB - 1) / SEARCH_WPB;
-    uint64_t cap = (uint64_t)num_sms * occ_cache;
+    int occ = occ_cache;
+    if (const char* ev = getenv("HNSWB200_SEARCH_BLOCKS_PER_SM")) {  // experiment knob
+        int v = atoi(ev);
+        if (v >= 1 && v < occ) occ = v;
+    }
+    uint64_t cap = (uint64_t)num_sms * occ;
     int grid = (int)(want < cap ? want : cap);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);

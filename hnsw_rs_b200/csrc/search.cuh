@@ -176,12 +176,12 @@ struct Vis16 {
     // an id to record).  Every lane executes every iteration of the one loop, so the warp never
     // splits into separately scheduled fragments.  Returns "id was new" per lane.
     __device__ __forceinline__ bool insert_warp(uint32_t id, bool want, bool* ovf) const {
-        const uint32_t bmask = (bbits >= 32) ? 0xFFFFFFFFu : ((1u << bbits) - 1u);
-        const uint32_t h = (id * 0x9E3779B1u) & bmask;
-        const uint32_t rbits = bbits - tbits;
-        const uint32_t rem16 = (h & ((1u << rbits) - 1u)) << 4;
+        // h = (id * odd) mod 2^B, kept top-aligned: the home slot is its top t bits, the remainder the next B-t
+        const uint32_t h = (id * 0x9E3779B1u) << (32u - bbits);
         const uint32_t tmask = (1u << tbits) - 1u;
-        uint32_t slot = h >> rbits, mine = rem16;  // mine = rem16 | displacement
+        // (h << t) holds the remainder in its top B-t bits and zeros below: this shift leaves it at bits [4, 4+B-t)
+        const uint32_t rem16 = (h << tbits) >> (28u - (bbits - tbits));
+        uint32_t slot = h >> (32u - tbits), mine = rem16;  // mine = rem16 | displacement
         bool pending = want, isnew = false;
 #pragma unroll 1
         while (__any_sync(HB_FULL, pending)) {

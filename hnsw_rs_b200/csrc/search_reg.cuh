@@ -119,6 +119,9 @@ __device__ __forceinline__ void search_query_reg(const Q& query, const uint8_t* 
     uint32_t nb = lane == 0 ? ep : EMPTY_ID;
     bool seed = false;
     uint32_t row = EMPTY_ID, next = EMPTY_ID, b0 = 0;
+    // adjacency geometry of the current layer
+    uint32_t S = layer ? g.SU : g.S0;
+    const uint32_t* adj = layer ? g.upper_adj : g.adj0;
 #pragma unroll 1
     while (true) {
         // ---- one batch of up to 32 ids: results.insert_visited(node) (results.rs:101-103) ----
@@ -183,7 +186,7 @@ __device__ __forceinline__ void search_query_reg(const Q& query, const uint8_t* 
         // ---- next batch ----
         if (row != EMPTY_ID) {  // more of the current adjacency row (rows wider than 32, continuation rows)
             b0 += 32;
-            if (b0 >= (layer ? g.SU : g.S0)) { row = next; next = EMPTY_ID; b0 = 0; }
+            if (b0 >= S) { row = next; next = EMPTY_ID; b0 = 0; }
         }
         seed = false;
         if (row == EMPTY_ID) {
@@ -193,6 +196,8 @@ __device__ __forceinline__ void search_query_reg(const Q& query, const uint8_t* 
                 L.clear_flags();
                 if (layer == 0) break;
                 --layer;
+                S = layer ? g.SU : g.S0;
+                adj = layer ? g.upper_adj : g.adj0;
                 ef_l = layer ? 1 : ef;
                 ef_lane = ef_l < 32 * KPL ? ef_l / KPL : -1;
                 ef_slot = ef_l % KPL;
@@ -210,8 +215,7 @@ __device__ __forceinline__ void search_query_reg(const Q& query, const uint8_t* 
             row = layer ? __ldg(g.upper_off + cid) + (layer - 1) : cid;
         }
         {
-            const uint32_t S = layer ? g.SU : g.S0;
-            const uint32_t* rp = (layer ? g.upper_adj : g.adj0) + (size_t)row * S;
+            const uint32_t* rp = adj + (size_t)row * S;
             const uint32_t i = b0 + lane;
             nb = (i < S) ? __ldg(rp + i) : EMPTY_ID;
             const bool ok = !(nb & CHAIN_BIT);
