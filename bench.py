@@ -13,7 +13,7 @@ e2e    = the same through the host-buffer entry point hnswb200_search (pinned ho
          ids / distances / counts out), host<->device copies inside the timed region.
 N > 1: the index is replicated, every rank searches its own 10,000 queries (weak scaling), and
 the ids are all-gathered over NCCL inside the timed region so that every rank holds all results
-(the gather of step s runs on NCCL's stream while step s+1 searches; two result buffers).
+(the gather of step s runs on NCCL's stream while the next steps search; one result buffer per step).
 """
 import argparse
 import ctypes as C
@@ -242,10 +242,11 @@ def main():
         search_dev(ef)
     torch.cuda.synchronize()
     if world > 1:
-        # the ids of step s are all-gathered (NCCL, its own stream) while step s+1 searches: two result buffers
-        ids2 = [d_ids, torch.empty_like(d_ids)]
-        gathered = [torch.empty((world * nq, K), dtype=torch.int32, device="cuda") for _ in range(2)]
-        pending = [None, None]
+        # the ids of step s are all-gathered (NCCL, its own stream) while the next steps search; every step has
+        # its own result buffer, so nothing in the search stream ever waits for a collective
+        ids2 = [torch.empty_like(d_ids) for _ in range(a.steps)]
+        gathered = [torch.empty((world * nq, K), dtype=torch.int32, device="cuda") for _ in range(a.steps)]
+        pending = []
         dist.all_gather_into_tensor(gathered[0], d_ids)
         dist.barrier()
     torch.cuda.synchronize()
@@ -255,18 +256,14 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for s in range(a.steps):
-        b = s & 1
-        if world > 1 and pending[b] is not None:
-            pending[b].wait()  # the buffer pair of step s-2 is free again
-        # no event between the launches: consecutive searches are programmatic dependent launches, the blocks
-        # of step s+1 take over the SMs that the last long queries of step s leave idle
-        search_dev(ef, ids2[b] if world > 1 else None)
+        # consecutive searches are programmatic dependent launches: the blocks of step s+1 take over the SMs
+        # that the last long queries of step s leave idle
+        search_dev(ef, ids2[s] if world > 1 else None)
         if world > 1:
-            pending[b] = dist.all_gather_into_tensor(gathered[b], ids2[b], async_op=True)
+            pending.append(dist.all_gather_into_tensor(gathered[s], ids2[s], async_op=True))
     if world > 1:
         for h in pending:
-            if h is not None:
-                h.wait()
+            h.wait()
     e1.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -321,6 +318,8 @@ def main():
         t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
+    search_dev(ef)
+    torch.cuda.synchronize()
     assert np.array_equal(h_ids.numpy(), d_ids.cpu().numpy()), "host and device entry points disagree"
     e2e = {"value": world * nq * a.steps / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": int(nq * dim * 4),
            "d2h_bytes_per_step": int(nq * K * 8 + nq * 4 + nq * 4)}

@@ -31,7 +31,10 @@ class HNSW:
 
     def __del__(self):
         if getattr(self, "h", None):
-            lib().hnswb200_index_destroy(self.h)
+            try:
+                lib().hnswb200_index_destroy(self.h)
+            except Exception:  # interpreter shutdown: the loader's modules may be gone already
+                pass
             self.h = None
 
     # ---- params -----------------------------------------------------------

@@ -73,7 +73,10 @@ class SimplePoints:
 
     def __del__(self):
         if getattr(self, "h", None) and self._owned:
-            lib().hnswb200_points_destroy(self.h)
+            try:
+                lib().hnswb200_points_destroy(self.h)
+            except Exception:  # interpreter shutdown
+                pass
             self.h = None
 
     @staticmethod
