@@ -1,0 +1,38 @@
+"""The reference's own tests restated in C++ (tests/cpp/reference_suite.cpp) against the C++ host mirror of its API
+(include/hnsw_rs.hpp) over the C ABI.  CPU: the suite builds, links and refuses to compute; GPU: it passes."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "tests", "cpp", "reference_suite")
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def _build():
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "tests", "cpp"), "-s"])
+
+
+def test_cpp_suite_builds_and_lists():
+    _build()
+    out = subprocess.run([BIN, GOLDEN, "--list"], capture_output=True, text=True, check=True).stdout.split()
+    assert "hnsw::hnsw_glove_build_eval" in out and "vectors::quant::distance" in out and len(out) == 12
+
+
+def test_cpp_suite_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    _build()
+    r = subprocess.run([BIN, GOLDEN], capture_output=True, text=True)
+    assert r.returncode != 0 and "no CUDA device" in r.stdout
+
+
+@pytest.mark.gpu
+def test_cpp_reference_suite_passes():
+    _build()
+    r = subprocess.run([BIN, GOLDEN], capture_output=True, text=True, timeout=600)
+    print(r.stdout)
+    assert r.returncode == 0, r.stdout[-2000:]
+    assert "12 passed; 0 failed" in r.stdout
