@@ -132,7 +132,26 @@ def pick_ef(search_fn, gt, efs):
     return chosen, table
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line, on the real stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    # stdout carries exactly one JSON line: everything libraries print while we run (NCCL's version banner, ...)
+    # is sent to stderr by pointing fd 1 at fd 2 for the duration of the run
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -167,7 +186,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: hnsw_rs_b200 has no CPU fallback "
                          "(the reference arm also builds its index with the device builder)")
     torch.cuda.set_device(local_rank)
-    os.environ["NCCL_DEBUG"] = os.environ.get("HNSWB200_NCCL_DEBUG", "WARN")  # keep NCCL's banner off stdout: ONE JSON line
+
     if world > 1 and a.impl == "b200":
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -359,7 +378,7 @@ def main():
         line = {"metric": "queries/sec at recall@10>=0.99", "value": value, "unit": "queries/s", "n_gpus": world,
                 "steps": a.steps, "warmup": a.warmup, "ms_per_step": total_ms / a.steps, "config": cfg, "e2e": e2e,
                 "roofline": roofline, "clocks": clocks, "note": "profiling helper run, no cpu_baseline"}
-        print(json.dumps(line), flush=True)
+        emit(line)
         if world > 1:
             dist.destroy_process_group()
         return 0
@@ -388,7 +407,7 @@ def main():
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": total_ms / a.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
             "e2e": e2e, "gpu_launches": a.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -417,7 +436,7 @@ def run_reference(a, ix, queries, gt, ef, rec, cfg):
             "cpu_baseline": {"value": value, "unit": "queries/s", "cores": cores, "kind": "port",
                              "sample": f"all {nq} queries per step at ef={ef}, {cores} threads"},
             "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
