@@ -486,3 +486,39 @@ def test_extend_loaded_index(H, oracle, tmp_path):
     ix.insert_bulk(b, batch=1)
     orc.insert_bulk(b)
     assert_same_graph([ix.export_layer(l) for l in range(ix.nb_layers())], orc.export_layers())
+
+
+# ---- BASELINE configs[1] at full size: size-independent properties ---------------------------------------
+def test_full_size_c2_properties(H, oracle):
+    """1,183,514 x 100 (the bench workload), built on the device: results are sorted by (dist, id), ids are unique,
+    every returned distance equals the batched distance kernel's value bit for bit, results do not depend on how the
+    queries are batched or on n, recall@10 >= 0.99 at ef = 64 against the exact ground truth, and a sample agrees with
+    the oracle searching the exported graph (ids, distances, hop and evaluation counters)."""
+    base = synth(1183514, 100, 2048, 1)
+    queries = synth(2000, 100, 2048, 2)
+    ix = H.HNSW.new(16, 200, 100).insert_bulk(base)
+    assert ix.len() == 1183514
+    ids, dists, counts, st = ix.ann_batch(queries, 10, 64, with_stats=True)
+    assert (counts == 10).all()
+    key = (bits(dists).astype(np.uint64) << np.uint64(32)) | ids.astype(np.uint64)
+    assert (key[:, 1:] > key[:, :-1]).all()                      # strictly ascending (dist, id): sorted and unique
+    for q in (0, 1, 777, 1999):                                  # distances are the kernel's own exact values
+        d = ix._points().dist_query_many(queries[q], ids[q])
+        assert np.array_equal(bits(d), bits(dists[q]))
+    ids2, dists2, _ = ix.ann_batch(queries, 10, 64)              # idempotent
+    assert np.array_equal(ids, ids2) and np.array_equal(bits(dists), bits(dists2))
+    sub = np.arange(0, 2000, 7)                                  # independent of the batch composition
+    ids3, _, _ = ix.ann_batch(queries[sub], 10, 64)
+    assert np.array_equal(ids3, ids[sub])
+    ids4, _, c4 = ix.ann_batch(queries[:300], 40, 64)            # n only truncates the list
+    assert (c4 == 40).all() and np.array_equal(ids4[:, :10], ids[:300])
+    gt, gd = H.bruteforce_topk(ix._points(), queries, 10)
+    hits = sum(len(set(gt[i].tolist()) & set(ids[i].tolist())) for i in range(len(queries)))
+    assert hits / gt.size >= 0.99
+    gkey = (bits(gd).astype(np.uint64) << np.uint64(32)) | gt.astype(np.uint64)
+    assert (gkey[:, 1:] > gkey[:, :-1]).all() and (gkey[:, 0] <= key[:, 0]).all()   # nothing beats the exact nearest
+    orc = to_oracle(oracle, ix)
+    o = orc.search_batch(queries[:200], 10, 64, threads=8)
+    ok = st["flags"][:200] == 0
+    assert np.array_equal(ids[:200], o[0]) and np.array_equal(bits(dists[:200]), bits(o[1]))
+    assert np.array_equal(st["hops"][:200], o[3]) and np.array_equal(st["evals"][:200][ok], o[4][ok])
