@@ -112,6 +112,7 @@ __device__ __forceinline__ float group_sum_sqrt(u64 acc, int gl, int gbase) {
 // ---------------------------------------------------------------------------
 template <int NCH, int REM>
 struct RegQuery {
+    static constexpr bool kKeepsSmem = false;  // the dequantised values are copied to registers by init()
     static constexpr int W = (int)hb_layout_W(NCH);
     static constexpr int TAIL = (int)hb_layout_tail(NCH, REM);
     static constexpr int RP = (REM + 1) / 2;  // remainder pairs
@@ -215,6 +216,7 @@ struct RegQuery {
 // Query held in shared memory, runtime dimension (any dim).
 // ---------------------------------------------------------------------------
 struct SmemQuery {
+    static constexpr bool kKeepsSmem = true;  // dist() reads the dequantised values from shared memory
     const float* qd;
     RecLayout L;
     __device__ __forceinline__ void init(const RecLayout& l, const float* q, int) {

@@ -375,9 +375,12 @@ __global__ void __launch_bounds__(SEARCH_WPB * 32, 5) search_kernel(SearchParams
 
 // The same query path on the register-resident list (ef <= 32*KPL): no shared-memory list, no
 // speculation; latency is hidden by warps (6 blocks of 4 warps per SM) instead.
-template <class VIS>
+// per warp: visited table | 32 candidate ids | 32 admitted keys | merge buffer (32*KPL keys) | dequantised query.
+// A register-resident query (RegQuery) needs its shared-memory copy only until init(): the merge buffer reuses it.
+template <class VIS, class Q, int KPL>
 __host__ __device__ inline size_t search_reg_warp_smem(uint32_t tbits, uint32_t qd_cap) {
-    return VIS::bytes(tbits) + 128 + (size_t)qd_cap * 4;
+    const size_t mb = (size_t)32 * KPL * 8, qb = ((size_t)qd_cap * 4 + 15) & ~(size_t)15;
+    return VIS::bytes(tbits) + 128 + 256 + (Q::kKeepsSmem ? mb + qb : (mb > qb ? mb : qb));
 }
 
 #ifndef HB_REG_MINB2
@@ -390,11 +393,13 @@ __global__ void __launch_bounds__(SEARCH_WPB * 32, reg_min_blocks(KPL)) search_k
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int gl = lane & 3, gbase = lane & ~3;
-    unsigned char* wsm = smem + (size_t)wib * search_reg_warp_smem<VIS>(p.tbits, p.qd_cap);
+    unsigned char* wsm = smem + (size_t)wib * search_reg_warp_smem<VIS, Q, KPL>(p.tbits, p.qd_cap);
     VIS vis;
     make_vis(vis, wsm, p);
     uint32_t* newbuf = reinterpret_cast<uint32_t*>(wsm + VIS::bytes(p.tbits));
-    float* qd = reinterpret_cast<float*>(newbuf + 32);
+    u64* kbuf = reinterpret_cast<u64*>(newbuf + 32);
+    u64* mbuf = kbuf + 32;
+    float* qd = reinterpret_cast<float*>(Q::kKeepsSmem ? mbuf + 32 * KPL : mbuf);
     // A following search (launched as programmatic dependent) reads nothing this grid writes: let its blocks
     // take over the SMs as soon as this grid's blocks retire, instead of waiting for the last long query.
     asm volatile("griddepcontrol.launch_dependents;");
@@ -426,7 +431,8 @@ __global__ void __launch_bounds__(SEARCH_WPB * 32, reg_min_blocks(KPL)) search_k
         q.init(p.L, qd, gl);
         SearchCounters cnt{0u, 0u, 0u, 0u};
         RegList<KPL> L;
-        search_query_reg<Q, VIS, KPL>(q, p.rec, p.L.stride, p.g, p.n_layers, p.ep, L, vis, newbuf, (int)p.ef, lane, cnt);
+        __syncwarp();  // every lane has copied its part of qd before the merge buffer may overwrite it
+        search_query_reg<Q, VIS, KPL>(q, p.rec, p.L.stride, p.g, p.n_layers, p.ep, L, vis, newbuf, kbuf, mbuf, (int)p.ef, lane, cnt);
         // get_top_selected(n)   (results.rs:59-61): position lane*KPL + s
         uint32_t mine = 0;
 #pragma unroll
@@ -455,7 +461,7 @@ __global__ void __launch_bounds__(SEARCH_WPB * 32, reg_min_blocks(KPL)) search_k
 
 template <class Q, class VIS, int KPL>
 static cudaError_t launch_search_reg_t(const SearchParams& p, int num_sms, cudaStream_t st, bool overlap_previous) {
-    size_t smem = search_reg_warp_smem<VIS>(p.tbits, p.qd_cap) * SEARCH_WPB;
+    size_t smem = search_reg_warp_smem<VIS, Q, KPL>(p.tbits, p.qd_cap) * SEARCH_WPB;
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
     static int occ_cache = 0;
     static size_t occ_smem = 0;
@@ -557,8 +563,9 @@ cudaError_t launch_search(const SearchLaunch& a, int num_sms, cudaStream_t st) {
     p.kpl = round_up((a.ef + 31) / 32, 2);
     if (!generic_list) {
         // register-resident list: ef <= 64 / 128 / 256 -> 2 / 4 / 8 keys per lane
-        auto rbytes = [&](uint32_t tb) {
-            return (use16 ? search_reg_warp_smem<Vis16>(tb, p.qd_cap) : search_reg_warp_smem<Vis32>(tb, p.qd_cap)) * SEARCH_WPB;
+        const uint32_t rkpl = a.ef <= 64 ? 2 : a.ef <= 128 ? 4 : 8;
+        auto rbytes = [&](uint32_t tb) {  // upper bound over the query classes
+            return ((use16 ? Vis16::bytes(tb) : Vis32::bytes(tb)) + 128 + 256 + (size_t)32 * rkpl * 8 + (size_t)p.qd_cap * 4 + 16) * SEARCH_WPB;
         };
         while (rbytes(p.tbits) > 200 * 1024 && p.tbits > 9 && (!use16 || p.bbits <= p.tbits - 1 + 12)) --p.tbits;
         if (!a.counter_is_fresh) {

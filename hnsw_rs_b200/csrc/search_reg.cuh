@@ -15,14 +15,10 @@
 // Key layout: (f32 bits of dist << 32) | (id << 1) | expanded.  ids are < 2^31, so id << 1 fits;
 // keys of different ids compare like Dist::cmp (graph/src/dist.rs:30-37) whatever their flag bits,
 // and a new key (flag clear) is never < an entry with the same (dist, id).  Position p of the
-// sorted list lives in lane p / KPL, slot p % KPL: an insertion moves keys inside a lane by
-// register renaming and hands one key to the next lane with a single shuffle.
+// sorted list lives in lane p / KPL, slot p % KPL.  The keys admitted while one batch of neighbours is
+// evaluated are merged in one step (RegList::merge): every key computes its final position by counting.
 #pragma once
 #include "search.cuh"
-
-#ifndef HB_PREFETCH_ROWS
-#define HB_PREFETCH_ROWS 0  // prefetch the layer-0 adjacency row of every key admitted to the list
-#endif
 
 namespace hb {
 
@@ -50,24 +46,48 @@ struct RegList {
         for (int t = 1; t < KPL; ++t) x = sel64(s == t, v[t], x);
         return __shfl_sync(HB_FULL, x, p / KPL);
     }
-    // Insert `key` (same value in all lanes, < the key at position ef-1) keeping the list sorted;
-    // the key at position ef (lane == ef_lane, slot ef_slot) is dropped.
-    __device__ __forceinline__ void insert(u64 key, int lane, int ef_lane, int ef_slot) {
-        int c = 0;
+    // Merge the m (<= 32) new keys kbuf[0..m) -- all different from each other and from the list's keys -- into
+    // the sorted list and keep the ef smallest: selected <- ef smallest of (selected U new), which is what the
+    // reference's one-by-one admission (searcher.rs:74-94) ends with, whatever the order.  Every key learns its
+    // final position by counting: a list key moves up by the number of new keys below it, a new key lands at
+    // (list keys below it) + (new keys below it); the permutation itself goes through mbuf (32*KPL slots of
+    // shared memory).  len = number of real keys, updated.
+    __device__ __forceinline__ void merge(const u64* kbuf, int m, u64* mbuf, int& len, int ef, int lane) {
+        const u64 nk = lane < m ? kbuf[lane] : RSENT;
+        int shift[KPL];
 #pragma unroll
-        for (int s = 0; s < KPL; ++s) c += (v[s] < key) ? 1 : 0;
-        const int l0 = __popc(__ballot_sync(HB_FULL, c == KPL));  // lanes before l0 hold smaller keys only
-        const u64 inc = __shfl_up_sync(HB_FULL, v[KPL - 1], 1);
-        // lanes after l0 move every slot up (slot 0 takes the previous lane's last key); lane l0
-        // moves the slots above c and puts the key into slot c; lanes before l0 keep their keys
-        c = lane > l0 ? -1 : (lane == l0 ? c : KPL);
-        const int ts = lane == ef_lane ? ef_slot : -1;
+        for (int s = 0; s < KPL; ++s) shift[s] = 0;
+        int own = 0, myr = 0;
+#pragma unroll 1
+        for (int j = 0; j < m; ++j) {
+            const u64 kj = kbuf[j];  // broadcast read
+            int r = 0;
 #pragma unroll
-        for (int s = KPL - 1; s >= 0; --s) {
-            u64 nv = sel64(s > c, s ? v[s ? s - 1 : 0] : inc, v[s]);
-            nv = sel64(s == c, key, nv);
-            v[s] = sel64(s == ts, RSENT, nv);
+            for (int s = 0; s < KPL; ++s) {
+                const bool lt = kj < v[s];  // also true for the sentinel slots
+                shift[s] += lt ? 1 : 0;
+                r += __popc(__ballot_sync(HB_FULL, !lt));
+            }
+            own += (kj < nk) ? 1 : 0;
+            myr = lane == j ? r : myr;
         }
+#pragma unroll
+        for (int s = 0; s < KPL; ++s) {
+            const int p = lane * KPL + s + shift[s];
+            if (v[s] != RSENT && p < ef) mbuf[p] = v[s];
+        }
+        if (lane < m) {
+            const int p = myr + own;
+            if (p < ef) mbuf[p] = nk;
+        }
+        __syncwarp();
+        len = min(ef, len + m);
+#pragma unroll
+        for (int s = 0; s < KPL; ++s) {
+            const int p = lane * KPL + s;
+            v[s] = p < len ? mbuf[p] : RSENT;
+        }
+        __syncwarp();
     }
     // candidates.pop_first(): the first entry whose "expanded" bit is clear; marks it expanded.
     // Returns false when there is none.
@@ -107,11 +127,12 @@ template <class Q, class VIS, int KPL>
 __device__ __forceinline__ void search_query_reg(const Q& query, const uint8_t* __restrict__ rec,
                                                  uint32_t rec_stride, const GraphView& g, uint32_t n_layers,
                                                  uint32_t ep, RegList<KPL>& L, const VIS& vis,
-                                                 uint32_t* newbuf, int ef, int lane, SearchCounters& cnt) {
+                                                 uint32_t* newbuf, u64* kbuf, u64* mbuf, int ef, int lane,
+                                                 SearchCounters& cnt) {
     const int gl = lane & 3, gbase = lane & ~3, grp = lane >> 2;
     uint32_t layer = n_layers - 1;
     int ef_l = layer ? 1 : ef;
-    int ef_lane = ef_l < 32 * KPL ? ef_l / KPL : -1, ef_slot = ef_l % KPL;
+    int len = 0;  // |selected|
     L.reset();
     u64 worst = RSENT;  // key at position ef_l - 1: the sentinel (max) while |selected| < ef_l
     vis.clear(lane);
@@ -157,6 +178,7 @@ __device__ __forceinline__ void search_query_reg(const Q& query, const uint8_t* 
                 }
             }
             __syncwarp();
+            int kcnt = 0;
 #pragma unroll 1
             for (int r0 = 0; r0 < ncnt; r0 += 8) {
                 const int idx = r0 + grp;
@@ -165,23 +187,20 @@ __device__ __forceinline__ void search_query_reg(const Q& query, const uint8_t* 
                 // index.get_point(node).dist2other(point)  (searcher.rs:66-69)
                 const float d = query.dist(rec + (size_t)cand * rec_stride, gl, gbase);
                 const u64 key = make_rkey(d, cand);
-                // admission (searcher.rs:74-94): key < list[ef-1] covers |selected| < ef and strict <
-                unsigned am = __ballot_sync(HB_FULL, act && gl == 0 && key < worst);
-#pragma unroll 1
-                while (am) {
-                    const int src = __ffs(am) - 1;
-                    am &= am - 1;
-                    const u64 k = __shfl_sync(HB_FULL, key, src);
-                    if (k < worst) {
-                        L.insert(k, lane, ef_lane, ef_slot);
-                        worst = L.get(ef_l - 1);
-                        // every node that is ever expanded was admitted first: request its adjacency row
-                        // now, so that the pop finds it in L2
-                        if (HB_PREFETCH_ROWS && layer == 0 && lane == 0) prefetch_l2(g.adj0 + (size_t)rkey_id(k) * g.S0);
-                    }
-                }
+                // admission (searcher.rs:74-94): key < list[ef-1] covers |selected| < ef and strict <.
+                // `worst` is the batch's starting value: a key admitted against it may still fall off the end
+                // in the merge, exactly as a later, nearer key would have evicted it one by one.
+                const bool want = act && gl == 0 && key < worst;
+                const unsigned am = __ballot_sync(HB_FULL, want);
+                if (want) kbuf[kcnt + __popc(am & ((1u << lane) - 1))] = key;
+                kcnt += __popc(am);
             }
             __syncwarp();
+            if (kcnt) {
+                L.merge(kbuf, kcnt, mbuf, len, ef_l, lane);
+                worst = len == ef_l ? mbuf[ef_l - 1] : RSENT;
+                __syncwarp();
+            }
         }
         // ---- next batch ----
         if (row != EMPTY_ID) {  // more of the current adjacency row (rows wider than 32, continuation rows)
@@ -199,9 +218,7 @@ __device__ __forceinline__ void search_query_reg(const Q& query, const uint8_t* 
                 S = layer ? g.SU : g.S0;
                 adj = layer ? g.upper_adj : g.adj0;
                 ef_l = layer ? 1 : ef;
-                ef_lane = ef_l < 32 * KPL ? ef_l / KPL : -1;
-                ef_slot = ef_l % KPL;
-                worst = L.get(ef_l - 1);
+                worst = len == ef_l ? L.get(ef_l - 1) : RSENT;
                 vis.clear(lane);
                 // seed batch: visited <- ids(selected); the upper layers ran with ef = 1, so the
                 // entry set is the single key at position 0
