@@ -54,23 +54,31 @@ struct RegList {
     // shared memory).  len = number of real keys, updated.
     __device__ __forceinline__ void merge(const u64* kbuf, int m, u64* mbuf, int& len, int ef, int lane) {
         const u64 nk = lane < m ? kbuf[lane] : RSENT;
-        int shift[KPL];
+        // bit j of ltm[s]: new key j is below this lane's list key s; bit j of ownm: new key j is below this
+        // lane's own new key; myr: number of list keys below this lane's own new key
+        uint32_t ltm[KPL];
 #pragma unroll
-        for (int s = 0; s < KPL; ++s) shift[s] = 0;
-        int own = 0, myr = 0;
+        for (int s = 0; s < KPL; ++s) ltm[s] = 0u;
+        uint32_t ownm = 0u;
+        int myr = 0;
 #pragma unroll 1
         for (int j = 0; j < m; ++j) {
             const u64 kj = kbuf[j];  // broadcast read
+            const uint32_t bit = 1u << j;
             int r = 0;
 #pragma unroll
             for (int s = 0; s < KPL; ++s) {
-                const bool lt = kj < v[s];  // also true for the sentinel slots
-                shift[s] += lt ? 1 : 0;
-                r += __popc(__ballot_sync(HB_FULL, !lt));
+                const bool ge = !(kj < v[s]);  // list key below the new key (keys are distinct); false for sentinels
+                r += __popc(__ballot_sync(HB_FULL, ge));
+                ltm[s] |= ge ? 0u : bit;
             }
-            own += (kj < nk) ? 1 : 0;
+            ownm |= (kj < nk) ? bit : 0u;
             myr = lane == j ? r : myr;
         }
+        int shift[KPL];
+#pragma unroll
+        for (int s = 0; s < KPL; ++s) shift[s] = __popc(ltm[s]);
+        const int own = __popc(ownm);
 #pragma unroll
         for (int s = 0; s < KPL; ++s) {
             const int p = lane * KPL + s + shift[s];
