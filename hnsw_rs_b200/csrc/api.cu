@@ -81,6 +81,9 @@ int hnswb200_ctx_create(int device, hnswb200_ctx** out) {
     c->own_stream = true;
     HB_CUDA(cudaMalloc((void**)&c->d_scratch, 64 * sizeof(uint32_t)));
     HB_CUDA(cudaMemset(c->d_scratch, 0, 64 * sizeof(uint32_t)));
+    HB_CUDA(cudaHostAlloc((void**)&c->h_status, 64, cudaHostAllocMapped));
+    HB_CUDA(cudaHostGetDevicePointer((void**)&c->d_status, c->h_status, 0));
+    c->h_status[0] = 0;
     HB_CUDA(cudaMalloc((void**)&c->d_counters, hnswb200_ctx::COUNTER_RING * sizeof(uint32_t)));
     HB_CUDA(cudaMemset(c->d_counters, 0, hnswb200_ctx::COUNTER_RING * sizeof(uint32_t)));
     *out = c;
@@ -93,6 +96,7 @@ void hnswb200_ctx_destroy(hnswb200_ctx* c) {
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     if (c->d_scratch) cudaFree(c->d_scratch);
     if (c->d_counters) cudaFree(c->d_counters);
+    if (c->h_status) cudaFreeHost(c->h_status);
     if (c->d_ws) cudaFree(c->d_ws);
     if (c->d_bf_ws) cudaFree(c->d_bf_ws);
     delete c;
@@ -710,10 +714,23 @@ static int search_check(const hnswb200_index* ix, uint64_t nq, uint32_t n, uint3
     return 0;
 }
 
+static int search_dev_impl(hnswb200_ctx* c, const hnswb200_index* ix, const float* d_queries, uint64_t nq,
+                           uint32_t n, uint32_t ef, uint32_t* d_out_ids, float* d_out_dists,
+                           uint32_t* d_out_counts, uint32_t* d_hops, uint32_t* d_evals, uint32_t* d_flags,
+                           uint32_t* d_nbrs, uint32_t* nan_any);
+
 int hnswb200_search_dev(hnswb200_ctx* c, const hnswb200_index* ix, const float* d_queries, uint64_t nq,
                         uint32_t n, uint32_t ef, uint32_t* d_out_ids, float* d_out_dists,
                         uint32_t* d_out_counts, uint32_t* d_hops, uint32_t* d_evals, uint32_t* d_flags,
                         uint32_t* d_nbrs) {
+    return search_dev_impl(c, ix, d_queries, nq, n, ef, d_out_ids, d_out_dists, d_out_counts, d_hops, d_evals, d_flags,
+                           d_nbrs, nullptr);
+}
+
+static int search_dev_impl(hnswb200_ctx* c, const hnswb200_index* ix, const float* d_queries, uint64_t nq,
+                           uint32_t n, uint32_t ef, uint32_t* d_out_ids, float* d_out_dists,
+                           uint32_t* d_out_counts, uint32_t* d_hops, uint32_t* d_evals, uint32_t* d_flags,
+                           uint32_t* d_nbrs, uint32_t* nan_any) {
     if (!c || !ix || (nq && (!d_queries || !d_out_ids))) return fail(HNSWB200_EINVAL, "search_dev: NULL argument");
     if (nq == 0) return 0;
     int rc = search_check(ix, nq, n, ef);
@@ -736,6 +753,7 @@ int hnswb200_search_dev(hnswb200_ctx* c, const hnswb200_index* ix, const float* 
     a.out_evals = d_evals;
     a.out_flags = d_flags;
     a.out_nbrs = d_nbrs;
+    a.nan_any = nan_any;
     // counter ring (engine.h): slot 0 follows a memset of the whole ring and is an ordinary launch; the other
     // slots are launched as programmatic dependents of whatever kernel precedes them in the stream
     const uint32_t slot = (uint32_t)(c->search_seq++ % hnswb200_ctx::COUNTER_RING);
@@ -758,36 +776,47 @@ int hnswb200_search(hnswb200_ctx* c, const hnswb200_index* ix, const float* quer
     int rc = search_check(ix, nq, n, ef);
     if (rc) return rc;
     if (c->use()) return HNSWB200_ECUDA;
-    // grow-only per-context workspace: no cudaMalloc on the steady-state query path
+    // Page-locked caller buffers are used in place: the kernel reads the queries and writes the results over
+    // PCIe itself (88 + 4*dim bytes per query, spread over the whole launch), so there is no staging copy before
+    // or after it.  Pageable buffers are staged through the grow-only per-context workspace (no cudaMalloc on
+    // the steady-state path either way).
     const size_t b_q = nq * dim * 4, b_ids = nq * (size_t)n * 4, b_u = nq * 4;
     auto al = [](size_t v) { return (v + 255) / 256 * 256; };
-    size_t total = al(b_q) + 2 * al(b_ids) + 5 * al(b_u);
-    if (c->ws_reserve(total)) return HNSWB200_ECUDA;
+    auto mapped = [](const void* host) -> void* {
+        if (!host || getenv("HNSWB200_NO_ZERO_COPY")) return nullptr;
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        return (at.type == cudaMemoryTypeHost) ? at.devicePointer : nullptr;
+    };
+    struct Buf { void* host; void* dev; size_t bytes; bool staged; };
+    uint32_t* st_hops = stats ? stats->hops : nullptr;
+    uint32_t* st_evals = stats ? stats->evals : nullptr;
+    uint32_t* st_flags = stats ? stats->flags : nullptr;
+    uint32_t* st_nbrs = stats ? stats->nbrs : nullptr;
+    Buf q{(void*)queries, mapped(queries), b_q, false};
+    Buf outs[7] = {{out_ids, mapped(out_ids), b_ids, false},   {out_dists, mapped(out_dists), b_ids, false},
+                   {out_counts, mapped(out_counts), b_u, false}, {st_hops, mapped(st_hops), b_u, false},
+                   {st_evals, mapped(st_evals), b_u, false},     {st_flags, mapped(st_flags), b_u, false},
+                   {st_nbrs, mapped(st_nbrs), b_u, false}};
+    size_t total = q.dev ? 0 : al(b_q);
+    for (Buf& b : outs)
+        if (b.host && !b.dev) total += al(b.bytes);
+    if (total && c->ws_reserve(total)) return HNSWB200_ECUDA;
     unsigned char* w = (unsigned char*)c->d_ws;
-    float* dq = (float*)w; w += al(b_q);
-    uint32_t* dids = (uint32_t*)w; w += al(b_ids);
-    float* dd = (float*)w; w += al(b_ids);
-    uint32_t* dcnt = (uint32_t*)w; w += al(b_u);
-    uint32_t* dhops = (uint32_t*)w; w += al(b_u);
-    uint32_t* devals = (uint32_t*)w; w += al(b_u);
-    uint32_t* dflags = (uint32_t*)w; w += al(b_u);
-    uint32_t* dnbrs = (uint32_t*)w;
-    HB_CUDA(cudaMemcpyAsync(dq, queries, b_q, cudaMemcpyHostToDevice, c->stream));
-    rc = hnswb200_search_dev(c, ix, dq, nq, n, ef, dids, dd, dcnt, dhops, devals, dflags, dnbrs);
+    if (!q.dev) { q.dev = w; w += al(b_q); q.staged = true; }
+    for (Buf& b : outs)
+        if (b.host && !b.dev) { b.dev = w; w += al(b.bytes); b.staged = true; }
+    c->h_status[0] = 0;
+    if (q.staged) HB_CUDA(cudaMemcpyAsync(q.dev, queries, b_q, cudaMemcpyHostToDevice, c->stream));
+    rc = search_dev_impl(c, ix, (const float*)q.dev, nq, n, ef, (uint32_t*)outs[0].dev, (float*)outs[1].dev,
+                         (uint32_t*)outs[2].dev, (uint32_t*)outs[3].dev, (uint32_t*)outs[4].dev, (uint32_t*)outs[5].dev,
+                         (uint32_t*)outs[6].dev, c->d_status);
     if (rc) return rc;
-    if (c->h_flags.size() < nq) c->h_flags.resize(nq);
-    uint32_t* flags = c->h_flags.data();
-    HB_CUDA(cudaMemcpyAsync(out_ids, dids, b_ids, cudaMemcpyDeviceToHost, c->stream));
-    if (out_dists) HB_CUDA(cudaMemcpyAsync(out_dists, dd, b_ids, cudaMemcpyDeviceToHost, c->stream));
-    if (out_counts) HB_CUDA(cudaMemcpyAsync(out_counts, dcnt, b_u, cudaMemcpyDeviceToHost, c->stream));
-    if (stats && stats->hops) HB_CUDA(cudaMemcpyAsync(stats->hops, dhops, b_u, cudaMemcpyDeviceToHost, c->stream));
-    if (stats && stats->evals) HB_CUDA(cudaMemcpyAsync(stats->evals, devals, b_u, cudaMemcpyDeviceToHost, c->stream));
-    if (stats && stats->nbrs) HB_CUDA(cudaMemcpyAsync(stats->nbrs, dnbrs, b_u, cudaMemcpyDeviceToHost, c->stream));
-    HB_CUDA(cudaMemcpyAsync(flags, dflags, b_u, cudaMemcpyDeviceToHost, c->stream));
+    for (Buf& b : outs)
+        if (b.staged) HB_CUDA(cudaMemcpyAsync(b.host, b.dev, b.bytes, cudaMemcpyDeviceToHost, c->stream));
     HB_CUDA(cudaStreamSynchronize(c->stream));
-    if (stats && stats->flags) memcpy(stats->flags, flags, b_u);
-    for (uint64_t i = 0; i < nq; ++i)
-        if (flags[i] & 1u) return fail(HNSWB200_EINVAL, "search: NaN in query " + std::to_string(i) + " (the reference panics in partial_cmp().unwrap())");
+    if (c->h_status[0])
+        return fail(HNSWB200_EINVAL, "search: NaN in a query (the reference panics in partial_cmp().unwrap())");
     return 0;
 }
 

@@ -46,6 +46,8 @@ struct hnswb200_ctx {
     size_t bf_ws_bytes = 0;
     int bf_ws_reserve(size_t bytes);
     std::vector<uint32_t> h_flags;
+    uint32_t* h_status = nullptr;   // pinned + mapped host word the search kernel raises on a NaN query
+    uint32_t* d_status = nullptr;   // its device alias
     int ws_reserve(size_t bytes);
     int use() const;                // cudaSetDevice
 };

@@ -284,6 +284,7 @@ struct SearchParams {
     uint32_t* out_flags;
     uint32_t* out_nbrs;
     uint32_t* work_counter;
+    uint32_t* nan_any;  // may be null; set to 1 when a query holds a NaN (may live in pinned host memory)
 };
 
 constexpr int SEARCH_WPB = 4;
@@ -325,7 +326,10 @@ __global__ void __launch_bounds__(SEARCH_WPB * 32, 5) search_kernel(SearchParams
         __syncwarp();
         // Point::new(vector): the query is quantised exactly like a stored point (template.rs:313)
         float mn, dl;
-        bool ok = warp_quantise(p.queries + (size_t)qi * p.L.dim, p.L.dim, lane, qd, nullptr, mn, dl);
+        // one read of the f32 query (it may live in pinned host memory: see hnswb200_search), then quantise in place
+        for (uint32_t i = lane; i < p.L.dim; i += 32) qd[i] = p.queries[(size_t)qi * p.L.dim + i];
+        __syncwarp();
+        bool ok = warp_quantise(qd, p.L.dim, lane, qd, nullptr, mn, dl);
         __syncwarp();
         uint32_t* oid = p.out_ids + (size_t)qi * p.topn;
         float* od = p.out_dists ? p.out_dists + (size_t)qi * p.topn : nullptr;
@@ -337,6 +341,7 @@ __global__ void __launch_bounds__(SEARCH_WPB * 32, 5) search_kernel(SearchParams
                 if (p.out_evals) p.out_evals[qi] = 0;
                 if (p.out_flags) p.out_flags[qi] = 1u;
                 if (p.out_nbrs) p.out_nbrs[qi] = 0;
+                if (p.nan_any) *reinterpret_cast<volatile uint32_t*>(p.nan_any) = 1u;
             }
             continue;
         }
@@ -412,7 +417,10 @@ __global__ void __launch_bounds__(SEARCH_WPB * 32, reg_min_blocks(KPL)) search_k
         __syncwarp();
         // Point::new(vector): the query is quantised exactly like a stored point (template.rs:313)
         float mn, dl;
-        bool ok = warp_quantise(p.queries + (size_t)qi * p.L.dim, p.L.dim, lane, qd, nullptr, mn, dl);
+        // one read of the f32 query (it may live in pinned host memory: see hnswb200_search), then quantise in place
+        for (uint32_t i = lane; i < p.L.dim; i += 32) qd[i] = p.queries[(size_t)qi * p.L.dim + i];
+        __syncwarp();
+        bool ok = warp_quantise(qd, p.L.dim, lane, qd, nullptr, mn, dl);
         __syncwarp();
         uint32_t* oid = p.out_ids + (size_t)qi * p.topn;
         float* od = p.out_dists ? p.out_dists + (size_t)qi * p.topn : nullptr;
@@ -424,6 +432,7 @@ __global__ void __launch_bounds__(SEARCH_WPB * 32, reg_min_blocks(KPL)) search_k
                 if (p.out_evals) p.out_evals[qi] = 0;
                 if (p.out_flags) p.out_flags[qi] = 1u;
                 if (p.out_nbrs) p.out_nbrs[qi] = 0;
+                if (p.nan_any) *reinterpret_cast<volatile uint32_t*>(p.nan_any) = 1u;
             }
             continue;
         }
@@ -557,6 +566,7 @@ cudaError_t launch_search(const SearchLaunch& a, int num_sms, cudaStream_t st) {
     p.out_ids = a.out_ids; p.out_dists = a.out_dists; p.out_counts = a.out_counts;
     p.out_hops = a.out_hops; p.out_evals = a.out_evals; p.out_flags = a.out_flags; p.out_nbrs = a.out_nbrs;
     p.work_counter = a.work_counter;
+    p.nan_any = a.nan_any;
     bool use16;
     choose_visited(a.ef, a.g.S0, a.n_points, &p.tbits, &p.bbits, &use16);
     const bool generic_list = a.ef > 256 || getenv("HNSWB200_GENERAL_PATH");  // env: test knob

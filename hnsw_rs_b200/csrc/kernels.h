@@ -32,6 +32,7 @@ struct SearchLaunch {
     uint32_t* out_evals;   // nq, may be null
     uint32_t* out_flags;   // nq, may be null (bit0 NaN query, bit1 visited overflow)
     uint32_t* out_nbrs = nullptr;  // nq, may be null: neighbour ids read
+    uint32_t* nan_any = nullptr;  // optional: set to 1 if any query holds a NaN
     uint32_t* work_counter;  // device u32, zero on entry
     bool counter_is_fresh = false;  // true: the caller guarantees *work_counter == 0 (no memset is enqueued)
     bool overlap_previous = false;  // launch as programmatic dependent of the previous kernel in the stream

@@ -522,3 +522,42 @@ def test_full_size_c2_properties(H, oracle):
     ok = st["flags"][:200] == 0
     assert np.array_equal(ids[:200], o[0]) and np.array_equal(bits(dists[:200]), bits(o[1]))
     assert np.array_equal(st["hops"][:200], o[3]) and np.array_equal(st["evals"][:200][ok], o[4][ok])
+
+
+def test_search_pinned_host_buffers_are_used_in_place(H, oracle, glove, glove_index, monkeypatch):
+    """hnswb200_search reads page-locked query buffers and writes page-locked result buffers in place (zero-copy over
+    PCIe); pageable buffers are staged.  Same answers either way, and a NaN query is still reported."""
+    import ctypes as C
+    import torch
+    from hnsw_rs_b200 import _ffi
+    _, queries = glove
+    ix = to_gpu(H, glove_index)
+    nq, dim = queries.shape
+    ref = ix.ann_batch(queries, 10, 60, with_stats=True)  # pageable numpy buffers: staged
+    hq = torch.from_numpy(queries.copy()).pin_memory()
+    hid = torch.zeros((nq, 10), dtype=torch.int32).pin_memory()
+    hd = torch.zeros((nq, 10), dtype=torch.float32).pin_memory()
+    hc = torch.zeros(nq, dtype=torch.int32).pin_memory()
+    hh = torch.zeros(nq, dtype=torch.int32).pin_memory()
+    he = torch.zeros(nq, dtype=torch.int32)  # one pageable statistic among pinned buffers
+    st = _ffi.SearchStats(C.cast(hh.data_ptr(), _ffi.u32p), C.cast(he.data_ptr(), _ffi.u32p), None, None)
+    lib = _ffi.lib()
+
+    def call():
+        _ffi.check(lib.hnswb200_search(ix.ctx.h, ix.h, C.cast(hq.data_ptr(), _ffi.f32p), nq, dim, 10, 60,
+                                       C.cast(hid.data_ptr(), _ffi.u32p), C.cast(hd.data_ptr(), _ffi.f32p),
+                                       C.cast(hc.data_ptr(), _ffi.u32p), C.byref(st)))
+    call()
+    assert np.array_equal(hid.numpy().view(np.uint32), ref[0]) and np.array_equal(bits(hd.numpy()), bits(ref[1]))
+    assert np.array_equal(hc.numpy().view(np.uint32), ref[2])
+    assert np.array_equal(hh.numpy().view(np.uint32), ref[3]["hops"]) and np.array_equal(he.numpy().view(np.uint32), ref[3]["evals"])
+    hid.zero_()
+    monkeypatch.setenv("HNSWB200_NO_ZERO_COPY", "1")
+    call()
+    monkeypatch.delenv("HNSWB200_NO_ZERO_COPY")
+    assert np.array_equal(hid.numpy().view(np.uint32), ref[0])
+    hq[3, 5] = float("nan")
+    with pytest.raises(H.HnswB200Error):
+        call()
+    hq[3, 5] = 0.0
+    call()  # the context recovers
