@@ -342,8 +342,8 @@ def main():
     assert np.array_equal(h_ids.numpy(), d_ids.cpu().numpy()), "host and device entry points disagree"
     e2e = {"value": world * nq * a.steps / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": int(nq * dim * 4),
            "d2h_bytes_per_step": int(nq * K * 8 + nq * 4),
-           "transfer": "hnswb200_search with page-locked host buffers: the kernel reads the queries and writes ids / "
-                       "distances / counts over PCIe in place (no staging copy); every step is synchronous"}
+           "transfer": "hnswb200_search with page-locked host buffers: first wave of queries by DMA, the others read in "
+                       "place by the kernel; ids / distances / counts written in place over PCIe; every step is synchronous"}
 
     if rank != 0:
         if world > 1:

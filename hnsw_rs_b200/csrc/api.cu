@@ -717,7 +717,7 @@ static int search_check(const hnswb200_index* ix, uint64_t nq, uint32_t n, uint3
 static int search_dev_impl(hnswb200_ctx* c, const hnswb200_index* ix, const float* d_queries, uint64_t nq,
                            uint32_t n, uint32_t ef, uint32_t* d_out_ids, float* d_out_dists,
                            uint32_t* d_out_counts, uint32_t* d_hops, uint32_t* d_evals, uint32_t* d_flags,
-                           uint32_t* d_nbrs, uint32_t* nan_any);
+                           uint32_t* d_nbrs, uint32_t* nan_any, const float* queries_tail = nullptr, uint32_t split = 0);
 
 int hnswb200_search_dev(hnswb200_ctx* c, const hnswb200_index* ix, const float* d_queries, uint64_t nq,
                         uint32_t n, uint32_t ef, uint32_t* d_out_ids, float* d_out_dists,
@@ -730,7 +730,7 @@ int hnswb200_search_dev(hnswb200_ctx* c, const hnswb200_index* ix, const float* 
 static int search_dev_impl(hnswb200_ctx* c, const hnswb200_index* ix, const float* d_queries, uint64_t nq,
                            uint32_t n, uint32_t ef, uint32_t* d_out_ids, float* d_out_dists,
                            uint32_t* d_out_counts, uint32_t* d_hops, uint32_t* d_evals, uint32_t* d_flags,
-                           uint32_t* d_nbrs, uint32_t* nan_any) {
+                           uint32_t* d_nbrs, uint32_t* nan_any, const float* queries_tail, uint32_t split) {
     if (!c || !ix || (nq && (!d_queries || !d_out_ids))) return fail(HNSWB200_EINVAL, "search_dev: NULL argument");
     if (nq == 0) return 0;
     int rc = search_check(ix, nq, n, ef);
@@ -754,6 +754,8 @@ static int search_dev_impl(hnswb200_ctx* c, const hnswb200_index* ix, const floa
     a.out_flags = d_flags;
     a.out_nbrs = d_nbrs;
     a.nan_any = nan_any;
+    a.queries_tail = queries_tail;
+    a.split = split;
     // counter ring (engine.h): slot 0 follows a memset of the whole ring and is an ordinary launch; the other
     // slots are launched as programmatic dependents of whatever kernel precedes them in the stream
     const uint32_t slot = (uint32_t)(c->search_seq++ % hnswb200_ctx::COUNTER_RING);
@@ -798,19 +800,25 @@ int hnswb200_search(hnswb200_ctx* c, const hnswb200_index* ix, const float* quer
                    {out_counts, mapped(out_counts), b_u, false}, {st_hops, mapped(st_hops), b_u, false},
                    {st_evals, mapped(st_evals), b_u, false},     {st_flags, mapped(st_flags), b_u, false},
                    {st_nbrs, mapped(st_nbrs), b_u, false}};
-    size_t total = q.dev ? 0 : al(b_q);
+    // The first wave of queries (one per resident warp) is wanted all at once when the kernel starts: those are
+    // copied by DMA; the rest of a page-locked query buffer is read in place, one query at a time, while others compute.
+    const uint64_t first_wave = std::min<uint64_t>(nq, (uint64_t)c->num_sms * 32);
+    const float* q_tail = nullptr;
+    if (q.dev && first_wave < nq) q_tail = (const float*)q.dev;
+    const size_t b_head = q.dev ? (q_tail ? first_wave * dim * 4 : 0) : b_q;
+    size_t total = al(b_head);
     for (Buf& b : outs)
         if (b.host && !b.dev) total += al(b.bytes);
     if (total && c->ws_reserve(total)) return HNSWB200_ECUDA;
     unsigned char* w = (unsigned char*)c->d_ws;
-    if (!q.dev) { q.dev = w; w += al(b_q); q.staged = true; }
+    if (b_head) { q.dev = w; w += al(b_head); q.staged = true; }
     for (Buf& b : outs)
         if (b.host && !b.dev) { b.dev = w; w += al(b.bytes); b.staged = true; }
     c->h_status[0] = 0;
-    if (q.staged) HB_CUDA(cudaMemcpyAsync(q.dev, queries, b_q, cudaMemcpyHostToDevice, c->stream));
+    if (q.staged) HB_CUDA(cudaMemcpyAsync(q.dev, queries, b_head, cudaMemcpyHostToDevice, c->stream));
     rc = search_dev_impl(c, ix, (const float*)q.dev, nq, n, ef, (uint32_t*)outs[0].dev, (float*)outs[1].dev,
                          (uint32_t*)outs[2].dev, (uint32_t*)outs[3].dev, (uint32_t*)outs[4].dev, (uint32_t*)outs[5].dev,
-                         (uint32_t*)outs[6].dev, c->d_status);
+                         (uint32_t*)outs[6].dev, c->d_status, q_tail, (uint32_t)first_wave);
     if (rc) return rc;
     for (Buf& b : outs)
         if (b.staged) HB_CUDA(cudaMemcpyAsync(b.host, b.dev, b.bytes, cudaMemcpyDeviceToHost, c->stream));

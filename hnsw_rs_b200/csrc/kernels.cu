@@ -272,6 +272,8 @@ struct SearchParams {
     GraphView g;
     uint32_t n_layers, ep;
     const float* queries;
+    const float* queries_tail;  // queries [split, nq) are read from here (same indexing); == queries when not split
+    uint32_t split;
     uint32_t nq, topn, ef;
     uint32_t kpl;           // keys per lane of the result list (capacity 32*kpl >= ef)
     uint32_t tbits, bbits;  // visited table: 2^tbits entries; ids < 2^bbits
@@ -327,7 +329,10 @@ __global__ void __launch_bounds__(SEARCH_WPB * 32, 5) search_kernel(SearchParams
         // Point::new(vector): the query is quantised exactly like a stored point (template.rs:313)
         float mn, dl;
         // one read of the f32 query (it may live in pinned host memory: see hnswb200_search), then quantise in place
-        for (uint32_t i = lane; i < p.L.dim; i += 32) qd[i] = p.queries[(size_t)qi * p.L.dim + i];
+        {
+            const float* src = (qi < p.split ? p.queries : p.queries_tail) + (size_t)qi * p.L.dim;
+            for (uint32_t i = lane; i < p.L.dim; i += 32) qd[i] = src[i];
+        }
         __syncwarp();
         bool ok = warp_quantise(qd, p.L.dim, lane, qd, nullptr, mn, dl);
         __syncwarp();
@@ -418,7 +423,10 @@ __global__ void __launch_bounds__(SEARCH_WPB * 32, reg_min_blocks(KPL)) search_k
         // Point::new(vector): the query is quantised exactly like a stored point (template.rs:313)
         float mn, dl;
         // one read of the f32 query (it may live in pinned host memory: see hnswb200_search), then quantise in place
-        for (uint32_t i = lane; i < p.L.dim; i += 32) qd[i] = p.queries[(size_t)qi * p.L.dim + i];
+        {
+            const float* src = (qi < p.split ? p.queries : p.queries_tail) + (size_t)qi * p.L.dim;
+            for (uint32_t i = lane; i < p.L.dim; i += 32) qd[i] = src[i];
+        }
         __syncwarp();
         bool ok = warp_quantise(qd, p.L.dim, lane, qd, nullptr, mn, dl);
         __syncwarp();
@@ -562,6 +570,8 @@ cudaError_t launch_search(const SearchLaunch& a, int num_sms, cudaStream_t st) {
     p.g.adj0 = a.g.adj0; p.g.S0 = a.g.S0; p.g.upper_off = a.g.upper_off; p.g.upper_adj = a.g.upper_adj; p.g.SU = a.g.SU;
     p.n_layers = a.g.n_layers; p.ep = a.ep;
     p.queries = a.queries; p.nq = a.nq; p.topn = a.topn; p.ef = a.ef;
+    p.queries_tail = a.queries_tail ? a.queries_tail : a.queries;
+    p.split = a.queries_tail ? a.split : a.nq;
     p.qd_cap = round_up(a.L.dim, 8) + 8;
     p.out_ids = a.out_ids; p.out_dists = a.out_dists; p.out_counts = a.out_counts;
     p.out_hops = a.out_hops; p.out_evals = a.out_evals; p.out_flags = a.out_flags; p.out_nbrs = a.out_nbrs;

@@ -24,6 +24,8 @@ struct SearchLaunch {
     uint32_t ep;
     uint64_t n_points;     // ids are < n_points (sizes the 16-bit visited table)
     const float* queries;  // device, nq * dim
+    const float* queries_tail = nullptr;  // optional second source for queries [split, nq) (mapped host memory)
+    uint32_t split = 0;
     uint32_t nq, topn, ef;
     uint32_t* out_ids;     // nq * topn (EMPTY padded)
     float* out_dists;      // nq * topn (+inf padded), may be null
