@@ -6,6 +6,6 @@ timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --save-index 
 for v in "$@"; do
   if [ $v = default ]; then unset HNSWB200_LIB; else export HNSWB200_LIB=$PWD/$v; fi
   for nq in 10000 100000; do
-    echo "variant $v nq $nq"; timeout 300 python tools/exp_search.py --load /tmp/ix --nq $nq --efs $EFS --oracle-sample 0 2>&1 | grep "ef="
+    echo "variant $v nq $nq"; timeout 300 python tools/dev/exp_search.py --load /tmp/ix --nq $nq --efs $EFS --oracle-sample 0 2>&1 | grep "ef="
   done
 done 2>&1 | tee gpurun_out/ab.log

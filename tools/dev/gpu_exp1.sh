@@ -8,6 +8,6 @@ tail -c 1500 gpurun_out/b.log
 for mode in reg smem; do
   if [ $mode = smem ]; then export HNSWB200_SMEM_LIST=1; else unset HNSWB200_SMEM_LIST; fi
   for nq in 10000 100000; do
-    echo "mode $mode nq $nq"; timeout 300 python tools/exp_search.py --load /tmp/ix --nq $nq --efs 64,100 --oracle-sample 300 2>&1 | grep "ef=\|parity"
+    echo "mode $mode nq $nq"; timeout 300 python tools/dev/exp_search.py --load /tmp/ix --nq $nq --efs 64,100 --oracle-sample 300 2>&1 | grep "ef=\|parity"
   done
 done 2>&1 | tee gpurun_out/exp1.log

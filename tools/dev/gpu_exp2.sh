@@ -4,5 +4,5 @@ mkdir -p gpurun_out
 timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --save-index /tmp/ix > gpurun_out/b.log 2>&1
 tail -c 600 gpurun_out/b.log; echo
 for nq in 10000 100000; do
-  echo "nq $nq"; timeout 300 python tools/exp_search.py --load /tmp/ix --nq $nq --efs ${EFS:-64,100} --oracle-sample ${OS:-300} 2>&1 | grep "ef=\|parity"
+  echo "nq $nq"; timeout 300 python tools/dev/exp_search.py --load /tmp/ix --nq $nq --efs ${EFS:-64,100} --oracle-sample ${OS:-300} 2>&1 | grep "ef=\|parity"
 done 2>&1 | tee gpurun_out/exp2.log
