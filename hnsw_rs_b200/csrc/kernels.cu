@@ -3,11 +3,13 @@
 //   K2 dist_*_kernel          <- distance_unrolled, dist2many, Points::distance/distance2point
 //                                (quant.rs:14-37, vectors/src/lib.rs:17-22, points/src/points.rs:86-101)
 //   K2f dist_full_pairs_kernel<- FullVec::distance             (vectors/src/full.rs:23-29)
-//   K3 search_kernel          <- HNSW::ann_by_vector + search_layer
+//   K3 search_kernel_reg      <- HNSW::ann_by_vector + search_layer, ef <= 256: result list in registers
+//      search_kernel             (search_reg.cuh); any ef: result list in shared memory (search.cuh)
 //                                (hnsw/src/template.rs:306-335, template/searcher.rs:23-103)
-//   K5 bf_chunk/bf_merge      <- brute_force_nns / sort_by_distance (hnsw/src/helpers/glove.rs:73-109)
+//   K5 bf_chunk/bf_merge      <- brute_force_nns / sort_by_distance (hnsw/src/helpers/glove.rs:73-109), exact
+//                                CUDA-core pass; the tensor-core filter for 128-byte records lives in bf_tc.cu
 //   K6 topk_merge_kernel      <- (no reference analogue) merge of per-shard top-k lists
-// All of them are HBM-bound byte/gather work; none is GEMM-shaped.
+// All kernels of this file are byte/gather work; the only dense contraction of the path is in bf_tc.cu.
 #include <stdio.h>
 #include <stdlib.h>
 

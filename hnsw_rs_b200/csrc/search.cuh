@@ -1,5 +1,6 @@
-// Warp-resident HNSW layer search (device side), shared by the query kernel and
-// the build kernel.
+// Warp-resident HNSW layer search with the result list in shared memory (any ef), used by the build
+// kernel (csrc/builder.cu) and by queries with ef > 256; plus the visited sets shared with the
+// register-list query path (csrc/search_reg.cuh, ef <= 256 -- the path bench.py measures).
 //
 // Restates Searcher::search_layer (hnsw/src/template/searcher.rs:23-103) over the
 // Results sets (hnsw/src/template/results.rs:26-33) with one warp per query:
