@@ -104,10 +104,12 @@ void hnswb200_ctx_destroy(hnswb200_ctx* c) {
 
 int hnswb200_ctx_set_stream(hnswb200_ctx* c, void* s) {
     if (!c) return fail(HNSWB200_EINVAL, "ctx is NULL");
-    if (c->own_stream && c->stream) {
-        cudaStreamSynchronize(c->stream);
-        cudaStreamDestroy(c->stream);
-    }
+    if (c->use()) return HNSWB200_ECUDA;
+    // work on the old stream may still use the counter ring and the workspaces: drain it, and make the next search
+    // start a fresh ring (its memset is ordered on the new stream)
+    cudaStreamSynchronize(c->stream);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    c->search_seq = 0;
     c->stream = (cudaStream_t)s;
     c->own_stream = false;
     return 0;
