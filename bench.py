@@ -13,7 +13,7 @@ e2e    = the same through the host-buffer entry point hnswb200_search (pinned ho
          ids / distances / counts out), host<->device copies inside the timed region.
 N > 1: the index is replicated, every rank searches its own 10,000 queries (weak scaling), and
 the ids are all-gathered over NCCL inside the timed region so that every rank holds all results
-(the gather of step s runs on NCCL's stream while the next steps search; one result buffer per step).
+(fused into the search kernel: peer stores over NVLink into every rank's buffer; NCCL only checks it).
 """
 import argparse
 import ctypes as C
@@ -225,9 +225,9 @@ def main():
     d_nb = torch.empty(nq, dtype=torch.int32, device="cuda")
     lib = _ffi.lib()
 
-    def search_dev(ef, ids=None):
-        _ffi.check(lib.hnswb200_search_dev(ctx.h, ix.h, dq.data_ptr(), nq, K, ef, (ids if ids is not None else d_ids).data_ptr(),
-                                           d_d.data_ptr(), d_cnt.data_ptr(), d_h.data_ptr(), d_e.data_ptr(), d_f.data_ptr(),
+    def search_dev(ef):
+        _ffi.check(lib.hnswb200_search_dev(ctx.h, ix.h, dq.data_ptr(), nq, K, ef, d_ids.data_ptr(), d_d.data_ptr(),
+                                           d_cnt.data_ptr(), d_h.data_ptr(), d_e.data_ptr(), d_f.data_ptr(),
                                            d_nb.data_ptr()))
 
     def search_ids(ef):
@@ -261,12 +261,12 @@ def main():
         search_dev(ef)
     torch.cuda.synchronize()
     if world > 1:
-        # the ids of step s are all-gathered (NCCL, its own stream) while the next steps search; every step has
-        # its own result buffer, so nothing in the search stream ever waits for a collective
-        ids2 = [torch.empty_like(d_ids) for _ in range(a.steps)]
-        gathered = [torch.empty((world * nq, K), dtype=torch.int32, device="cuda") for _ in range(a.steps)]
-        pending = []
-        dist.all_gather_into_tensor(gathered[0], d_ids)
+        # the all-gather is fused into the search kernel: every rank stores its id rows straight into the result
+        # buffer of every other rank (CUDA IPC mapping, NVLink / NVSwitch peer stores) while its other queries compute
+        from hnsw_rs_b200 import sharded
+        pg = sharded.PeerGather(ctx, nq, K)
+        reference_gather = torch.empty((world * nq, K), dtype=torch.int32, device="cuda")
+        dist.all_gather_into_tensor(reference_gather, d_ids)  # NCCL, outside the timed region: the checker of the fused path
         dist.barrier()
     torch.cuda.synchronize()
     sampler = ClockSampler(local_rank)
@@ -277,18 +277,21 @@ def main():
     for s in range(a.steps):
         # consecutive searches are programmatic dependent launches: the blocks of step s+1 take over the SMs
         # that the last long queries of step s leave idle
-        search_dev(ef, ids2[s] if world > 1 else None)
         if world > 1:
-            pending.append(dist.all_gather_into_tensor(gathered[s], ids2[s], async_op=True))
-    if world > 1:
-        for h in pending:
-            h.wait()
+            pg.search(ix, dq.data_ptr(), nq, ef, d_ids.data_ptr(), d_d.data_ptr(), d_cnt.data_ptr())
+        else:
+            search_dev(ef)
     e1.record()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     total_ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        got = torch.from_numpy(pg.download().view(np.int32)).cuda()
+        assert torch.equal(got, reference_gather), "fused all-gather differs from the NCCL all-gather"
+        dist.barrier()
+        pg.close()
     # the search kernel's launch duration, on its own (not overlapped with a neighbour): mean over the same
     # number of launches, each bracketed by events (an event between two launches serialises them)
     k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]

@@ -108,6 +108,16 @@ extern "C" {
                                ef: u32, d_out_ids: *mut u32, d_out_dists: *mut f32, d_out_counts: *mut u32,
                                d_hops: *mut u32, d_evals: *mut u32, d_flags: *mut u32, d_nbrs: *mut u32) -> c_int;
 
+    pub fn hnswb200_search_dev_gather(ctx: *mut hnswb200_ctx, ix: *const hnswb200_index, d_queries: *const f32, nq: u64,
+                                      n: u32, ef: u32, d_out_ids: *mut u32, d_out_dists: *mut f32, d_out_counts: *mut u32,
+                                      n_peers: u32, peer_ids: *const *mut u32, row_offset: u64) -> c_int;
+    pub fn hnswb200_dev_alloc(ctx: *mut hnswb200_ctx, bytes: u64, out: *mut *mut c_void) -> c_int;
+    pub fn hnswb200_dev_free(ctx: *mut hnswb200_ctx, ptr: *mut c_void) -> c_int;
+    pub fn hnswb200_dev_download(ctx: *mut hnswb200_ctx, d_src: *const c_void, host_dst: *mut c_void, bytes: u64) -> c_int;
+    pub fn hnswb200_ipc_export(ctx: *mut hnswb200_ctx, d_ptr: *mut c_void, handle: *mut u8) -> c_int;
+    pub fn hnswb200_ipc_open(ctx: *mut hnswb200_ctx, handle: *const u8, out: *mut *mut c_void) -> c_int;
+    pub fn hnswb200_ipc_close(ctx: *mut hnswb200_ctx, ptr: *mut c_void) -> c_int;
+
     pub fn hnswb200_bruteforce_topk(ctx: *mut hnswb200_ctx, base: *const hnswb200_points, queries: *const f32, nq: u64,
                                     k: u32, id_offset: u32, out_ids: *mut u32, out_dists: *mut f32) -> c_int;
     pub fn hnswb200_bruteforce_topk_dev(ctx: *mut hnswb200_ctx, base: *const hnswb200_points, d_queries: *const f32,

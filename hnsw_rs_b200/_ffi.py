@@ -81,6 +81,14 @@ SIGNATURES = {
     "hnswb200_search": (C.c_int, [vp, vp, f32p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, u32p, f32p,
                                   u32p, C.POINTER(SearchStats)]),
     "hnswb200_search_dev": (C.c_int, [vp, vp, vp, C.c_uint64, C.c_uint32, C.c_uint32, vp, vp, vp, vp, vp, vp, vp]),
+    "hnswb200_search_dev_gather": (C.c_int, [vp, vp, vp, C.c_uint64, C.c_uint32, C.c_uint32, vp, vp, vp, C.c_uint32,
+                                             C.POINTER(vp), C.c_uint64]),
+    "hnswb200_dev_alloc": (C.c_int, [vp, C.c_uint64, C.POINTER(vp)]),
+    "hnswb200_dev_free": (C.c_int, [vp, vp]),
+    "hnswb200_dev_download": (C.c_int, [vp, vp, vp, C.c_uint64]),
+    "hnswb200_ipc_export": (C.c_int, [vp, vp, u8p]),
+    "hnswb200_ipc_open": (C.c_int, [vp, u8p, C.POINTER(vp)]),
+    "hnswb200_ipc_close": (C.c_int, [vp, vp]),
     "hnswb200_bruteforce_topk": (C.c_int, [vp, vp, f32p, C.c_uint64, C.c_uint32, C.c_uint32, u32p, f32p]),
     "hnswb200_bruteforce_topk_dev": (C.c_int, [vp, vp, vp, C.c_uint64, C.c_uint32, C.c_uint32, vp, vp]),
     "hnswb200_topk_merge": (C.c_int, [vp, u32p, f32p, C.c_uint32, C.c_uint64, C.c_uint32, u32p, f32p]),

@@ -719,7 +719,8 @@ static int search_check(const hnswb200_index* ix, uint64_t nq, uint32_t n, uint3
 static int search_dev_impl(hnswb200_ctx* c, const hnswb200_index* ix, const float* d_queries, uint64_t nq,
                            uint32_t n, uint32_t ef, uint32_t* d_out_ids, float* d_out_dists,
                            uint32_t* d_out_counts, uint32_t* d_hops, uint32_t* d_evals, uint32_t* d_flags,
-                           uint32_t* d_nbrs, uint32_t* nan_any, const float* queries_tail = nullptr, uint32_t split = 0);
+                           uint32_t* d_nbrs, uint32_t* nan_any, const float* queries_tail = nullptr, uint32_t split = 0,
+                           uint32_t n_peers = 0, uint32_t* const* peer_ids = nullptr, uint64_t peer_row0 = 0);
 
 int hnswb200_search_dev(hnswb200_ctx* c, const hnswb200_index* ix, const float* d_queries, uint64_t nq,
                         uint32_t n, uint32_t ef, uint32_t* d_out_ids, float* d_out_dists,
@@ -732,7 +733,8 @@ int hnswb200_search_dev(hnswb200_ctx* c, const hnswb200_index* ix, const float* 
 static int search_dev_impl(hnswb200_ctx* c, const hnswb200_index* ix, const float* d_queries, uint64_t nq,
                            uint32_t n, uint32_t ef, uint32_t* d_out_ids, float* d_out_dists,
                            uint32_t* d_out_counts, uint32_t* d_hops, uint32_t* d_evals, uint32_t* d_flags,
-                           uint32_t* d_nbrs, uint32_t* nan_any, const float* queries_tail, uint32_t split) {
+                           uint32_t* d_nbrs, uint32_t* nan_any, const float* queries_tail, uint32_t split,
+                           uint32_t n_peers, uint32_t* const* peer_ids, uint64_t peer_row0) {
     if (!c || !ix || (nq && (!d_queries || !d_out_ids))) return fail(HNSWB200_EINVAL, "search_dev: NULL argument");
     if (nq == 0) return 0;
     int rc = search_check(ix, nq, n, ef);
@@ -758,6 +760,9 @@ static int search_dev_impl(hnswb200_ctx* c, const hnswb200_index* ix, const floa
     a.nan_any = nan_any;
     a.queries_tail = queries_tail;
     a.split = split;
+    a.n_peers = n_peers;
+    for (uint32_t g = 0; g < n_peers && g < hb::HB_MAX_PEERS; ++g) a.peer_ids[g] = peer_ids[g];
+    a.peer_row0 = peer_row0;
     // counter ring (engine.h): slot 0 follows a memset of the whole ring and is an ordinary launch; the other
     // slots are launched as programmatic dependents of whatever kernel precedes them in the stream
     const uint32_t slot = (uint32_t)(c->search_seq++ % hnswb200_ctx::COUNTER_RING);
@@ -766,6 +771,63 @@ static int search_dev_impl(hnswb200_ctx* c, const hnswb200_index* ix, const floa
     a.counter_is_fresh = true;
     a.overlap_previous = slot != 0 && !getenv("HNSWB200_NO_PDL");
     HB_CUDA(launch_search(a, c->num_sms, c->stream));
+    return 0;
+}
+
+int hnswb200_search_dev_gather(hnswb200_ctx* c, const hnswb200_index* ix, const float* d_queries, uint64_t nq,
+                               uint32_t n, uint32_t ef, uint32_t* d_out_ids, float* d_out_dists, uint32_t* d_out_counts,
+                               uint32_t n_peers, uint32_t* const* peer_ids, uint64_t row_offset) {
+    if (n_peers > hb::HB_MAX_PEERS) return fail(HNSWB200_EINVAL, "search_dev_gather: at most 8 peer buffers");
+    if (n_peers && !peer_ids) return fail(HNSWB200_EINVAL, "search_dev_gather: NULL peer list");
+    for (uint32_t g = 0; g < n_peers; ++g)
+        if (!peer_ids[g]) return fail(HNSWB200_EINVAL, "search_dev_gather: NULL peer buffer");
+    return search_dev_impl(c, ix, d_queries, nq, n, ef, d_out_ids, d_out_dists, d_out_counts, nullptr, nullptr, nullptr,
+                           nullptr, nullptr, nullptr, 0, n_peers, peer_ids, row_offset);
+}
+
+// ---- device buffers that other processes of the box can write (CUDA IPC over NVLink / NVSwitch) ----
+int hnswb200_dev_alloc(hnswb200_ctx* c, uint64_t bytes, void** out) {
+    if (!c || !out) return fail(HNSWB200_EINVAL, "dev_alloc: NULL argument");
+    if (c->use()) return HNSWB200_ECUDA;
+    HB_CUDA(cudaMalloc(out, bytes ? bytes : 1));
+    HB_CUDA(cudaMemsetAsync(*out, 0xFF, bytes, c->stream));
+    HB_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+int hnswb200_dev_free(hnswb200_ctx* c, void* p) {
+    if (!c) return fail(HNSWB200_EINVAL, "dev_free: NULL context");
+    if (c->use()) return HNSWB200_ECUDA;
+    if (p) HB_CUDA(cudaFree(p));
+    return 0;
+}
+int hnswb200_dev_download(hnswb200_ctx* c, const void* d_src, void* host_dst, uint64_t bytes) {
+    if (!c || !d_src || !host_dst) return fail(HNSWB200_EINVAL, "dev_download: NULL argument");
+    if (c->use()) return HNSWB200_ECUDA;
+    HB_CUDA(cudaMemcpyAsync(host_dst, d_src, bytes, cudaMemcpyDeviceToHost, c->stream));
+    HB_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+int hnswb200_ipc_export(hnswb200_ctx* c, void* d_ptr, uint8_t handle[64]) {
+    if (!c || !d_ptr || !handle) return fail(HNSWB200_EINVAL, "ipc_export: NULL argument");
+    if (c->use()) return HNSWB200_ECUDA;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    HB_CUDA(cudaIpcGetMemHandle(&h, d_ptr));
+    memcpy(handle, &h, 64);
+    return 0;
+}
+int hnswb200_ipc_open(hnswb200_ctx* c, const uint8_t handle[64], void** out) {
+    if (!c || !handle || !out) return fail(HNSWB200_EINVAL, "ipc_open: NULL argument");
+    if (c->use()) return HNSWB200_ECUDA;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    HB_CUDA(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+int hnswb200_ipc_close(hnswb200_ctx* c, void* p) {
+    if (!c) return fail(HNSWB200_EINVAL, "ipc_close: NULL context");
+    if (c->use()) return HNSWB200_ECUDA;
+    if (p) HB_CUDA(cudaIpcCloseMemHandle(p));
     return 0;
 }
 

@@ -289,7 +289,17 @@ struct SearchParams {
     uint32_t* out_nbrs;
     uint32_t* work_counter;
     uint32_t* nan_any;  // may be null; set to 1 when a query holds a NaN (may live in pinned host memory)
+    // fused all-gather of the id rows: row (peer_row0 + q) of every peer buffer also receives the ids of query q
+    // (peer memory mapped into this device: stores travel over NVLink while the other queries keep computing)
+    uint32_t* peer_ids[HB_MAX_PEERS];
+    uint32_t n_peers;
+    uint64_t peer_row0;
 };
+
+__device__ __forceinline__ void put_id(const SearchParams& p, uint32_t* oid, uint32_t qi, uint32_t j, uint32_t v) {
+    oid[j] = v;
+    for (uint32_t g = 0; g < p.n_peers; ++g) p.peer_ids[g][(p.peer_row0 + qi) * p.topn + j] = v;
+}
 
 constexpr int SEARCH_WPB = 4;
 
@@ -341,7 +351,7 @@ __global__ void __launch_bounds__(SEARCH_WPB * 32, 5) search_kernel(SearchParams
         uint32_t* oid = p.out_ids + (size_t)qi * p.topn;
         float* od = p.out_dists ? p.out_dists + (size_t)qi * p.topn : nullptr;
         if (!ok) {  // NaN in query: the reference panics; report through flags and an empty result
-            for (uint32_t j = lane; j < p.topn; j += 32) { oid[j] = EMPTY_ID; if (od) od[j] = INFINITY; }
+            for (uint32_t j = lane; j < p.topn; j += 32) { put_id(p, oid, qi, j, EMPTY_ID); if (od) od[j] = INFINITY; }
             if (lane == 0) {
                 if (p.out_counts) p.out_counts[qi] = 0;
                 if (p.out_hops) p.out_hops[qi] = 0;
@@ -370,7 +380,7 @@ __global__ void __launch_bounds__(SEARCH_WPB * 32, 5) search_kernel(SearchParams
             u64 k = (j < p.topn && j < p.ef) ? L.list[j] : SENTINEL;
             bool real = k != SENTINEL;
             if (j < p.topn) {
-                oid[j] = real ? (uint32_t)k : EMPTY_ID;
+                put_id(p, oid, qi, j, real ? (uint32_t)k : EMPTY_ID);
                 if (od) od[j] = real ? __uint_as_float((uint32_t)(k >> 32)) : INFINITY;
             }
             got += __popc(__ballot_sync(HB_FULL, real));
@@ -435,7 +445,7 @@ __global__ void __launch_bounds__(SEARCH_WPB * 32, reg_min_blocks(KPL)) search_k
         uint32_t* oid = p.out_ids + (size_t)qi * p.topn;
         float* od = p.out_dists ? p.out_dists + (size_t)qi * p.topn : nullptr;
         if (!ok) {  // NaN in query: the reference panics; report through flags and an empty result
-            for (uint32_t j = lane; j < p.topn; j += 32) { oid[j] = EMPTY_ID; if (od) od[j] = INFINITY; }
+            for (uint32_t j = lane; j < p.topn; j += 32) { put_id(p, oid, qi, j, EMPTY_ID); if (od) od[j] = INFINITY; }
             if (lane == 0) {
                 if (p.out_counts) p.out_counts[qi] = 0;
                 if (p.out_hops) p.out_hops[qi] = 0;
@@ -460,12 +470,12 @@ __global__ void __launch_bounds__(SEARCH_WPB * 32, reg_min_blocks(KPL)) search_k
             if (j < p.topn) {
                 const u64 k = L.v[s];
                 const bool real = (j < p.ef) && (k != RSENT);
-                oid[j] = real ? rkey_id(k) : EMPTY_ID;
+                put_id(p, oid, qi, j, real ? rkey_id(k) : EMPTY_ID);
                 if (od) od[j] = real ? __uint_as_float((uint32_t)(k >> 32)) : INFINITY;
                 mine += real ? 1u : 0u;
             }
         }
-        for (uint32_t j = 32 * KPL + lane; j < p.topn; j += 32) { oid[j] = EMPTY_ID; if (od) od[j] = INFINITY; }
+        for (uint32_t j = 32 * KPL + lane; j < p.topn; j += 32) { put_id(p, oid, qi, j, EMPTY_ID); if (od) od[j] = INFINITY; }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(HB_FULL, mine, o);
         if (lane == 0) {
@@ -579,6 +589,9 @@ cudaError_t launch_search(const SearchLaunch& a, int num_sms, cudaStream_t st) {
     p.out_hops = a.out_hops; p.out_evals = a.out_evals; p.out_flags = a.out_flags; p.out_nbrs = a.out_nbrs;
     p.work_counter = a.work_counter;
     p.nan_any = a.nan_any;
+    p.n_peers = a.n_peers < HB_MAX_PEERS ? a.n_peers : HB_MAX_PEERS;
+    for (uint32_t g = 0; g < HB_MAX_PEERS; ++g) p.peer_ids[g] = g < p.n_peers ? a.peer_ids[g] : nullptr;
+    p.peer_row0 = a.peer_row0;
     bool use16;
     choose_visited(a.ef, a.g.S0, a.n_points, &p.tbits, &p.bbits, &use16);
     const bool generic_list = a.ef > 256 || getenv("HNSWB200_GENERAL_PATH");  // env: test knob

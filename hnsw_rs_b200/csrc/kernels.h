@@ -17,6 +17,8 @@ struct DevGraph {
     uint32_t n_layers = 0;
 };
 
+constexpr uint32_t HB_MAX_PEERS = 8;  // GPUs of one box
+
 struct SearchLaunch {
     const uint8_t* rec;
     RecLayout L;
@@ -35,6 +37,9 @@ struct SearchLaunch {
     uint32_t* out_flags;   // nq, may be null (bit0 NaN query, bit1 visited overflow)
     uint32_t* out_nbrs = nullptr;  // nq, may be null: neighbour ids read
     uint32_t* nan_any = nullptr;  // optional: set to 1 if any query holds a NaN
+    uint32_t* peer_ids[HB_MAX_PEERS] = {};  // fused all-gather targets (device-visible peer buffers)
+    uint32_t n_peers = 0;
+    uint64_t peer_row0 = 0;
     uint32_t* work_counter;  // device u32, zero on entry
     bool counter_is_fresh = false;  // true: the caller guarantees *work_counter == 0 (no memset is enqueued)
     bool overlap_previous = false;  // launch as programmatic dependent of the previous kernel in the stream

@@ -136,3 +136,66 @@ class BaseShardedSearch:
         gi = all_gather_rows(np.ascontiguousarray(ids, np.uint32), self.group, self.device)
         gd = all_gather_rows(np.ascontiguousarray(dists, np.float32), self.group, self.device)
         return self.merge(gi, gd)
+
+
+class PeerGather:
+    """Fused all-gather for the query-sharded path: every rank owns one device buffer of world * rows_per_rank result
+    rows and maps the buffers of all the other ranks of the box (CUDA IPC, peer access over NVLink / NVSwitch).
+    hnswb200_search_dev_gather then stores the id row of local query q to row rank * rows_per_rank + q of EVERY buffer
+    while the other queries keep computing: no collective kernel, no extra launch.  After the ranks have synchronised
+    (stream sync + barrier) every buffer holds all results."""
+
+    def __init__(self, ctx, rows_per_rank, n, group=None):
+        import ctypes as C
+        from ._ffi import check, lib, vp
+        dist = _dist()
+        self.ctx, self.group, self.rows, self.n = ctx, group, int(rows_per_rank), int(n)
+        self.rank, self.world = _world(group)
+        if self.world > 8:
+            raise ValueError("PeerGather: at most 8 ranks (one box)")
+        self.bytes = self.world * self.rows * self.n * 4
+        self.local = vp()
+        check(lib().hnswb200_dev_alloc(ctx.h, self.bytes, C.byref(self.local)))
+        handle = (C.c_uint8 * 64)()
+        check(lib().hnswb200_ipc_export(ctx.h, self.local, handle))
+        handles = [None] * self.world
+        if self.world > 1:
+            dist.all_gather_object(handles, bytes(handle), group=group)
+        self._opened = []
+        ptrs = []
+        for r in range(self.world):
+            if r == self.rank:
+                ptrs.append(self.local.value)
+                continue
+            p = vp()
+            check(lib().hnswb200_ipc_open(ctx.h, (C.c_uint8 * 64).from_buffer_copy(handles[r]), C.byref(p)))
+            self._opened.append(p)
+            ptrs.append(p.value)
+        self.ptrs = (vp * self.world)(*ptrs)
+
+    def search(self, index, d_queries_ptr, nq, ef, d_ids_ptr, d_dists_ptr=None, d_counts_ptr=None):
+        """Asynchronous on the context's stream: search nq (<= rows_per_rank) device-resident queries, results to the
+        local buffers given AND to this rank's rows of every peer buffer."""
+        from ._ffi import check, lib
+        if nq > self.rows:
+            raise ValueError("PeerGather.search: more queries than rows per rank")
+        check(lib().hnswb200_search_dev_gather(self.ctx.h, index.h, d_queries_ptr, nq, self.n, ef, d_ids_ptr, d_dists_ptr,
+                                               d_counts_ptr, self.world, self.ptrs, self.rank * self.rows))
+
+    def download(self):
+        """ids[world * rows_per_rank, n] as this rank sees them (call after stream sync + barrier)."""
+        import ctypes as C
+        from ._ffi import check, lib, u32p
+        out = np.empty((self.world * self.rows, self.n), np.uint32)
+        check(lib().hnswb200_dev_download(self.ctx.h, self.local, out.ctypes.data_as(C.c_void_p), self.bytes))
+        return out
+
+    def close(self):
+        """Unmap the peers and free the local buffer; every rank must be past its last use (barrier first)."""
+        from ._ffi import check, lib
+        for p in self._opened:
+            check(lib().hnswb200_ipc_close(self.ctx.h, p))
+        self._opened = []
+        if self.local:
+            check(lib().hnswb200_dev_free(self.ctx.h, self.local))
+            self.local = None

@@ -149,6 +149,23 @@ int hnswb200_search_dev(hnswb200_ctx* ctx, const hnswb200_index* ix, const float
                         uint32_t* d_out_counts, uint32_t* d_hops, uint32_t* d_evals, uint32_t* d_flags,
                         uint32_t* d_nbrs);
 
+/* The same search with the all-gather of the results fused into it (query-sharded, replicated index): the id row of
+ * query q is also stored to row row_offset + q of each of the n_peers (<= 8) buffers in peer_ids -- device pointers
+ * valid on this context's device, typically the other ranks' result buffers opened with hnswb200_ipc_open, so the
+ * stores travel over NVLink / NVSwitch while the other queries keep computing.  No reference analogue. */
+int hnswb200_search_dev_gather(hnswb200_ctx* ctx, const hnswb200_index* ix, const float* d_queries, uint64_t nq,
+                               uint32_t n, uint32_t ef, uint32_t* d_out_ids, float* d_out_dists,
+                               uint32_t* d_out_counts, uint32_t n_peers, uint32_t* const* peer_ids,
+                               uint64_t row_offset);
+/* device buffers that the other processes of the box can write: plain cudaMalloc memory (filled with 0xFF) and its
+ * CUDA IPC handle (64 bytes); ipc_open maps a peer's buffer into this context's device with peer access enabled */
+int hnswb200_dev_alloc(hnswb200_ctx* ctx, uint64_t bytes, void** out);
+int hnswb200_dev_free(hnswb200_ctx* ctx, void* ptr);
+int hnswb200_dev_download(hnswb200_ctx* ctx, const void* d_src, void* host_dst, uint64_t bytes);
+int hnswb200_ipc_export(hnswb200_ctx* ctx, void* d_ptr, uint8_t handle[64]);
+int hnswb200_ipc_open(hnswb200_ctx* ctx, const uint8_t handle[64], void** out);
+int hnswb200_ipc_close(hnswb200_ctx* ctx, void* ptr);
+
 /* brute_force_nns (hnsw/src/helpers/glove.rs:73-109): exact top-k under the quantised metric with
  * (dist, id) order.  id_offset is added to every returned id (global ids of a base shard). */
 int hnswb200_bruteforce_topk(hnswb200_ctx* ctx, const hnswb200_points* base, const float* queries,
