@@ -16,10 +16,10 @@
 // re-evaluated with the exact arithmetic (csrc/dist.cuh) and merged under (dist, id) by bf_merge_kernel.
 // Top-k ids and distances are therefore bit-identical to the CUDA-core path and to the oracle.
 //
-// Kernel shape (one CTA per SM, 10 warps): a tile of 256 base records stays in shared memory (TMA,
+// Kernel shape (one CTA per SM, 2 + 16 warps): a tile of 256 base records stays in shared memory (TMA,
 // SWIZZLE_128B, K-major); tiles of 128 queries stream through a 3-stage TMA ring; one thread issues
 // 4 x tcgen05.mma (M=128, N=256, K=32) per query tile into one of two 256-column TMEM accumulators;
-// 8 epilogue warps read the accumulator with tcgen05.ld (32 lanes x 32 columns), form the estimate with
+// 16 epilogue warps read the accumulator with tcgen05.ld (32 lanes x 32 columns), form the estimate with
 // packed f32x2 FMAs and append survivors to the per-query candidate lists.
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -39,7 +39,11 @@ constexpr int TC_M = 128;       // queries per tile (TMEM lanes)
 constexpr int TC_N = 256;       // base records per tile (TMEM columns)
 constexpr int TC_K = 128;       // bytes per record = K extent
 constexpr int TC_STAGES = 3;    // query-tile ring
-constexpr int TC_EPI_WARPS = 8;
+#ifndef HB_TC_EPI_WARPS
+#define HB_TC_EPI_WARPS 16
+#endif
+constexpr int TC_EPI_WARPS = HB_TC_EPI_WARPS;     // 4 TMEM lane quarters x (TC_EPI_WARPS / 4) column groups
+constexpr int TC_COLS_PER_WARP = TC_N / (TC_EPI_WARPS / 4);
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr uint32_t TC_A_BYTES = TC_M * TC_K;  // 16 KB
 constexpr uint32_t TC_B_BYTES = TC_N * TC_K;  // 32 KB
@@ -153,11 +157,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bf_tc_filter_kernel(const __gri
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (warp >= 2) {  // per-column constants of the stationary base tile
-        const int c = threadIdx.x - 64;
-        const uint64_t row = tile_row0 + c;
-        float4 k = make_float4(0.f, 0.f, 0.f, INFINITY);  // rows past the chunk never survive
-        if (row < p.row_end) k = __ldg(p.bconst + row);
-        S.cu[c] = k.x; S.cv[c] = k.y; S.cw[c] = k.z; S.cb[c] = k.w;
+        for (int c = threadIdx.x - 64; c < TC_N; c += 32 * TC_EPI_WARPS) {
+            const uint64_t row = tile_row0 + c;
+            float4 k = make_float4(0.f, 0.f, 0.f, INFINITY);  // rows past the chunk never survive
+            if (row < p.row_end) k = __ldg(p.bconst + row);
+            S.cu[c] = k.x; S.cv[c] = k.y; S.cw[c] = k.z; S.cb[c] = k.w;
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -198,8 +203,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bf_tc_filter_kernel(const __gri
             }
         }
     } else {
-        // ===== epilogue: 8 warps; warp w reads TMEM lanes 32*(w%4).., columns 128*half.. =====
-        const int quarter = warp & 3, half = (warp - 2) >> 2;
+        // ===== epilogue: warp w reads TMEM lanes 32*(w%4).., columns TC_COLS_PER_WARP*cgroup.. =====
+        const int quarter = warp & 3, cgroup = (warp - 2) >> 2;
         uint32_t it = 0;
         for (uint32_t t = blockIdx.y; t < p.nq_tiles; t += gridDim.y, ++it) {
             const uint32_t acc = it & 1, aph = (it >> 1) & 1;
@@ -209,8 +214,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bf_tc_filter_kernel(const __gri
             mbar_wait(&S.acc_full[acc], aph);
             tc_fence_after();
 #pragma unroll 1
-            for (int ch = 0; ch < 4; ++ch) {
-                const int col0 = half * 128 + ch * 32;
+            for (int ch = 0; ch < TC_COLS_PER_WARP / 32; ++ch) {
+                const int col0 = cgroup * TC_COLS_PER_WARP + ch * 32;
                 uint32_t v[32];
                 asm volatile(
                     "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
