@@ -138,15 +138,29 @@ struct RegQuery {
         return magic_byte(word32(w[pz / 16], (pz % 16) / 4), pz % 4);
     }
 
-    __device__ __forceinline__ float dist(const uint8_t* __restrict__ rec, int gl, int gbase) const {
-        const uint4* p = reinterpret_cast<const uint4*>(rec);
+    // the bytes of one record that this lane needs, in registers (lets a caller issue the loads of several
+    // records before it evaluates the first)
+    struct Rec {
         uint4 w[W];
+        uint4 tw;
+    };
+    __device__ __forceinline__ static Rec load(const uint8_t* __restrict__ rec, int gl) {
+        const uint4* p = reinterpret_cast<const uint4*>(rec);
+        Rec r;
 #pragma unroll
-        for (int j = 0; j < W; ++j) w[j] = __ldg(p + 4 * j + gl);
-        uint4 tw = make_uint4(0, 0, 0, 0);
+        for (int j = 0; j < W; ++j) r.w[j] = __ldg(p + 4 * j + gl);
+        r.tw = make_uint4(0, 0, 0, 0);
+        if (TAIL) r.tw = __ldg(p + 4 * W);
+        return r;
+    }
+    __device__ __forceinline__ float dist(const uint8_t* __restrict__ rec, int gl, int gbase) const {
+        return dist(load(rec, gl), gl, gbase);
+    }
+    __device__ __forceinline__ float dist(const Rec& R, int gl, int gbase) const {
+        const uint4 (&w)[W] = R.w;
+        const uint4 tw = R.tw;
         float mn, dl;
         if (TAIL) {
-            tw = __ldg(p + 4 * W);
             mn = __uint_as_float(tw.x);
             dl = __uint_as_float(tw.y);
         } else {
@@ -223,6 +237,9 @@ struct SmemQuery {
         qd = q;
         L = l;
     }
+    struct Rec { const uint8_t* p; };  // runtime dimension: nothing is preloaded
+    __device__ __forceinline__ static Rec load(const uint8_t* __restrict__ rec, int) { return Rec{rec}; }
+    __device__ __forceinline__ float dist(const Rec& r, int gl, int gbase) const { return dist(r.p, gl, gbase); }
     __device__ __forceinline__ float dist(const uint8_t* __restrict__ rec, int gl, int gbase) const {
         const uint4* p = reinterpret_cast<const uint4*>(rec);
         const float mn = __ldg(reinterpret_cast<const float*>(rec + hb_min_offset(L)));

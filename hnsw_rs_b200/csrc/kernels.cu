@@ -148,12 +148,17 @@ __global__ void __launch_bounds__(128) dist_query_many_kernel(const uint8_t* __r
     q.init(L, qd, gl);
     const uint64_t warp = (uint64_t)blockIdx.x * (blockDim.x >> 5) + wib;
     const uint64_t nwarps = (uint64_t)gridDim.x * (blockDim.x >> 5);
-    for (uint64_t base = warp * 8; base < n; base += nwarps * 8) {
-        uint64_t i = base + grp;
-        bool act = i < n;
-        uint32_t id = __ldg(ids + (act ? i : base));
-        float d = q.dist(rec + (size_t)id * L.stride, gl, gbase);
-        if (act && gl == 0) out[i] = d;
+    // two rounds of 8 candidates per iteration: the loads of the second are in flight while the first is evaluated
+    for (uint64_t base = warp * 16; base < n; base += nwarps * 16) {
+        const uint64_t i0 = base + grp, i1 = base + 8 + grp;
+        const bool a0 = i0 < n, a1 = i1 < n;
+        const uint32_t id0 = __ldg(ids + (a0 ? i0 : base)), id1 = __ldg(ids + (a1 ? i1 : base));
+        const typename Q::Rec r0 = Q::load(rec + (size_t)id0 * L.stride, gl);
+        const typename Q::Rec r1 = Q::load(rec + (size_t)id1 * L.stride, gl);
+        const float d0 = q.dist(r0, gl, gbase);
+        const float d1 = q.dist(r1, gl, gbase);
+        if (a0 && gl == 0) out[i0] = d0;
+        if (a1 && gl == 0) out[i1] = d1;
     }
 }
 
@@ -163,7 +168,7 @@ cudaError_t launch_dist_query_many(const uint8_t* rec, const RecLayout& L, const
     if (n == 0) return cudaSuccess;
     const uint32_t qd_cap = (L.dim + 7) / 8 * 8 + 8;
     size_t smem = (size_t)4 * qd_cap * 4;
-    int grid = grid_for_warps((n + 7) / 8, 4, 148 * 8);
+    int grid = grid_for_warps((n + 15) / 16, 4, 148 * 8);
     HB_DISPATCH_DIM(L, {
         cudaFuncSetAttribute(dist_query_many_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         dist_query_many_kernel<Q><<<grid, 128, smem, st>>>(rec, L, query, ids, n, out, nan_flag);
