@@ -20,6 +20,10 @@
 #pragma once
 #include "search.cuh"
 
+#ifndef HB_PREFETCH_ALL
+#define HB_PREFETCH_ALL 1  // 0: only the records of rounds >= 2 are prefetched, after the visited test
+#endif
+
 namespace hb {
 
 constexpr u64 RSENT = ~0ull;
@@ -155,6 +159,15 @@ __device__ __forceinline__ void search_query_reg(const Q& query, const uint8_t* 
     while (true) {
         // ---- one batch of up to 32 ids: results.insert_visited(node) (results.rs:101-103) ----
         const bool valid = !(nb & CHAIN_BIT);  // EMPTY_ID and chain markers carry bit 31
+#if HB_PREFETCH_ALL
+        // request the record of every neighbour before the visited test: the memory latency overlaps the hash probing
+        // (about half of the neighbours turn out to be visited already: DRAM has the headroom, the issue slots do not)
+        if (valid) {
+            const uint8_t* rp8 = rec + (size_t)nb * rec_stride;
+            prefetch_l2(rp8);
+            if (rec_stride > 128) prefetch_l2(rp8 + 128);
+        }
+#endif
         bool ovf = false;
         bool isnew = vis.insert_warp(nb, valid, &ovf);
         if (__any_sync(HB_FULL, ovf)) {
@@ -179,7 +192,7 @@ __device__ __forceinline__ void search_query_reg(const Q& query, const uint8_t* 
                 newbuf[my] = nb;
                 // records of the second and later rounds are requested now, so that those rounds
                 // do not pay a second memory latency
-                if (my >= 8) {
+                if (!HB_PREFETCH_ALL && my >= 8) {
                     const uint8_t* rp8 = rec + (size_t)nb * rec_stride;
                     prefetch_l2(rp8);
                     if (rec_stride > 128) prefetch_l2(rp8 + 128);
