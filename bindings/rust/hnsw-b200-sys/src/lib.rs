@@ -12,6 +12,8 @@ pub const HNSWB200_EIO: c_int = -3;
 pub const HNSWB200_ENOMEM: c_int = -4;
 pub const HNSWB200_ESTATE: c_int = -5;
 pub const HNSWB200_NO_ID: u32 = 0xFFFF_FFFF;
+pub const HNSWB200_METRIC_L2: c_int = 0;
+pub const HNSWB200_METRIC_COSINE: c_int = 1;
 
 #[repr(C)] pub struct hnswb200_ctx { _p: [u8; 0] }
 #[repr(C)] pub struct hnswb200_points { _p: [u8; 0] }
@@ -54,6 +56,11 @@ extern "C" {
     // vectors crate
     pub fn hnswb200_quantise(ctx: *mut hnswb200_ctx, rows: *const f32, n: u64, dim: u32, codes: *mut u8,
                              mins: *mut f32, deltas: *mut f32) -> c_int;
+    pub fn hnswb200_normalise(ctx: *mut hnswb200_ctx, rows: *const f32, n: u64, dim: u32, out: *mut f32) -> c_int;
+    pub fn hnswb200_points_set_metric(p: *mut hnswb200_points, metric: c_int) -> c_int;
+    pub fn hnswb200_points_metric(p: *const hnswb200_points) -> c_int;
+    pub fn hnswb200_index_set_metric(ix: *mut hnswb200_index, metric: c_int) -> c_int;
+    pub fn hnswb200_index_metric(ix: *const hnswb200_index) -> c_int;
     pub fn hnswb200_dist_full_pairs(ctx: *mut hnswb200_ctx, x: *const f32, y: *const f32, n: u64, dim: u32,
                                     out: *mut f32) -> c_int;
 

@@ -9,9 +9,9 @@ from .helpers import brute_force_nns, bruteforce_topk, load_glove_array, topk_me
 from .hnsw import HNSW
 from .params import Params, get_default_ml
 from .points import Point, SimplePoints, new_layer
-from .vectors import FullVec, QuantVec, gen_rand_vecs, quantise_rows
+from .vectors import FullVec, QuantVec, gen_rand_vecs, normalise_rows, quantise_rows
 
 __all__ = ["Context", "HnswB200Error", "NO_ID", "LIB_PATH", "lib", "Dist", "Graph", "GraphError", "Layers",
            "brute_force_nns", "bruteforce_topk", "load_glove_array", "topk_merge", "HNSW", "Params",
            "get_default_ml", "Point", "SimplePoints", "new_layer", "FullVec", "QuantVec", "gen_rand_vecs",
-           "quantise_rows"]
+           "quantise_rows", "normalise_rows"]

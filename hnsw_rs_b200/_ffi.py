@@ -49,6 +49,11 @@ SIGNATURES = {
     "hnswb200_ctx_device": (C.c_int, [vp]),
     "hnswb200_params_default": (None, [C.c_uint64, C.c_int64, C.c_uint64, C.POINTER(Params)]),
     "hnswb200_quantise": (C.c_int, [vp, f32p, C.c_uint64, C.c_uint32, u8p, f32p, f32p]),
+    "hnswb200_normalise": (C.c_int, [vp, f32p, C.c_uint64, C.c_uint32, f32p]),
+    "hnswb200_points_set_metric": (C.c_int, [vp, C.c_int]),
+    "hnswb200_points_metric": (C.c_int, [vp]),
+    "hnswb200_index_set_metric": (C.c_int, [vp, C.c_int]),
+    "hnswb200_index_metric": (C.c_int, [vp]),
     "hnswb200_dist_full_pairs": (C.c_int, [vp, f32p, f32p, C.c_uint64, C.c_uint32, f32p]),
     "hnswb200_points_upload": (C.c_int, [vp, u8p, f32p, f32p, u8p, C.c_uint64, C.c_uint32, C.POINTER(vp)]),
     "hnswb200_points_from_f32": (C.c_int, [vp, f32p, C.c_uint64, C.c_uint32, u8p, C.POINTER(vp)]),

@@ -40,6 +40,15 @@ int hnswb200_ctx::ws_reserve(size_t bytes) {
     return 0;
 }
 
+int hnswb200_ctx::norm_ws_reserve(size_t bytes) {
+    if (bytes <= norm_ws_bytes) return 0;
+    if (d_norm_ws) { cudaStreamSynchronize(stream); cudaFree(d_norm_ws); d_norm_ws = nullptr; norm_ws_bytes = 0; }
+    cudaError_t e = cudaMalloc(&d_norm_ws, bytes + bytes / 4);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(normalised-query workspace)");
+    norm_ws_bytes = bytes + bytes / 4;
+    return 0;
+}
+
 int hnswb200_ctx::bf_ws_reserve(size_t bytes) {
     if (bytes <= bf_ws_bytes) return 0;
     if (d_bf_ws) { cudaStreamSynchronize(stream); cudaFree(d_bf_ws); d_bf_ws = nullptr; bf_ws_bytes = 0; }
@@ -99,6 +108,7 @@ void hnswb200_ctx_destroy(hnswb200_ctx* c) {
     if (c->h_status) cudaFreeHost(c->h_status);
     if (c->d_ws) cudaFree(c->d_ws);
     if (c->d_bf_ws) cudaFree(c->d_bf_ws);
+    if (c->d_norm_ws) cudaFree(c->d_norm_ws);
     delete c;
 }
 
@@ -163,6 +173,29 @@ int hnswb200_quantise(hnswb200_ctx* c, const float* rows, uint64_t n, uint32_t d
     return 0;
 }
 
+int hnswb200_normalise(hnswb200_ctx* c, const float* rows, uint64_t n, uint32_t dim, float* out) {
+    if (!c || (n && (!rows || !out)) || dim == 0) return fail(HNSWB200_EINVAL, "normalise: bad argument");
+    if (n == 0) return 0;
+    if (c->use()) return HNSWB200_ECUDA;
+    DevBuf<float> d;
+    HB_CUDA(d.alloc(n * dim));
+    HB_CUDA(cudaMemcpyAsync(d.p, rows, n * dim * 4, cudaMemcpyHostToDevice, c->stream));
+    HB_CUDA(launch_normalise(d.p, n, dim, d.p, c->stream));
+    HB_CUDA(cudaMemcpyAsync(out, d.p, n * dim * 4, cudaMemcpyDeviceToHost, c->stream));
+    HB_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int hnswb200_points_set_metric(hnswb200_points* p, int metric) {
+    if (!p) return fail(HNSWB200_EINVAL, "points_set_metric: NULL argument");
+    if (metric != HNSWB200_METRIC_L2 && metric != HNSWB200_METRIC_COSINE) return fail(HNSWB200_EINVAL, "unknown metric");
+    if (p->n != 0 && metric != p->metric)
+        return fail(HNSWB200_ESTATE, "the metric can only be chosen while the points object is empty (stored rows are already quantised)");
+    p->metric = metric;
+    return 0;
+}
+int hnswb200_points_metric(const hnswb200_points* p) { return p ? p->metric : -1; }
+
 int hnswb200_dist_full_pairs(hnswb200_ctx* c, const float* x, const float* y, uint64_t n, uint32_t dim,
                              float* out) {
     if (!c || !x || !y || !out) return fail(HNSWB200_EINVAL, "dist_full_pairs: NULL argument");
@@ -226,6 +259,7 @@ int hb::points_append_f32(hnswb200_ctx* c, hnswb200_points* p, const float* rows
     for (uint64_t s = 0; s < n; s += CH) {
         uint64_t cnt = std::min(CH, n - s);
         HB_CUDA(cudaMemcpyAsync(d_rows.p, rows + s * p->L.dim, cnt * p->L.dim * 4, cudaMemcpyHostToDevice, c->stream));
+        if (p->metric == HNSWB200_METRIC_COSINE) HB_CUDA(launch_normalise(d_rows.p, cnt, p->L.dim, d_rows.p, c->stream));
         HB_CUDA(launch_quantise(d_rows.p, cnt, p->L, p->d_rec + (p->n + s) * p->L.stride, nullptr, nullptr,
                                 nullptr, nan_flag, c->stream));
     }
@@ -345,6 +379,7 @@ int hnswb200_dist_query_many(hnswb200_ctx* c, const hnswb200_points* p, const fl
     HB_CUDA(cudaMemsetAsync(nan_flag, 0, 4, c->stream));
     HB_CUDA(cudaMemcpyAsync(dids.p, ids, n * 4, cudaMemcpyHostToDevice, c->stream));
     HB_CUDA(cudaMemcpyAsync(dq.p, query, p->L.dim * 4, cudaMemcpyHostToDevice, c->stream));
+    if (p->metric == HNSWB200_METRIC_COSINE) HB_CUDA(launch_normalise(dq.p, 1, p->L.dim, dq.p, c->stream));
     HB_CUDA(launch_dist_query_many(p->d_rec, p->L, dq.p, dids.p, n, dout.p, nan_flag, c->stream));
     HB_CUDA(cudaMemcpyAsync(out, dout.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
     uint32_t flag = 0;
@@ -695,6 +730,12 @@ void hnswb200_index_destroy(hnswb200_index* ix) {
     hnswb200_graph_destroy(ix->graph);
     delete ix;
 }
+int hnswb200_index_set_metric(hnswb200_index* ix, int metric) {
+    if (!ix) return fail(HNSWB200_EINVAL, "index_set_metric: NULL argument");
+    return hnswb200_points_set_metric(ix->points, metric);
+}
+int hnswb200_index_metric(const hnswb200_index* ix) { return ix ? ix->points->metric : -1; }
+
 int hnswb200_index_params(const hnswb200_index* ix, hnswb200_params* out) {
     if (!ix || !out) return fail(HNSWB200_EINVAL, "index_params: NULL argument");
     *out = ix->params;
@@ -741,6 +782,18 @@ static int search_dev_impl(hnswb200_ctx* c, const hnswb200_index* ix, const floa
     if (rc) return rc;
     if (c->use()) return HNSWB200_ECUDA;
     SearchLaunch a;
+    if (ix->points->metric == HNSWB200_METRIC_COSINE) {
+        // cosine: search the unit-norm copy of the queries (both sources of a split batch are merged into it)
+        const uint32_t dim = ix->points->L.dim;
+        if (c->norm_ws_reserve(nq * dim * 4)) return HNSWB200_ECUDA;
+        float* nqz = (float*)c->d_norm_ws;
+        const uint64_t head = queries_tail ? std::min<uint64_t>(split, nq) : nq;
+        HB_CUDA(launch_normalise(d_queries, head, dim, nqz, c->stream));
+        if (head < nq) HB_CUDA(launch_normalise(queries_tail + head * dim, nq - head, dim, nqz + head * dim, c->stream));
+        d_queries = nqz;
+        queries_tail = nullptr;
+        split = 0;
+    }
     a.rec = ix->points->d_rec;
     a.L = ix->points->L;
     a.g = ix->graph->view();
@@ -919,7 +972,8 @@ int hnswb200_bruteforce_topk_dev(hnswb200_ctx* c, const hnswb200_points* base, c
     const size_t o_qrec = cv.take(nq * L.stride), o_topk = cv.take(nq * k * 8), o_tau = cv.take(nq * 8),
                  o_buf = cv.take(nq * (size_t)cap * 8), o_cnt = cv.take(nq * 4),
                  o_bconst = cv.take(use_tc ? N * 16 : 0), o_qstat = cv.take(use_tc ? nq * 16 : 0),
-                 o_qconst = cv.take(use_tc ? nq_pad * 16 : 0), o_amask = cv.take(use_tc ? nq_pad * 128 : 0);
+                 o_qconst = cv.take(use_tc ? nq_pad * 16 : 0), o_amask = cv.take(use_tc ? nq_pad * 128 : 0),
+                 o_qnorm = cv.take(base->metric == HNSWB200_METRIC_COSINE ? nq * L.dim * 4 : 0);
     if (c->bf_ws_reserve(cv.off)) return HNSWB200_ECUDA;
     unsigned char* W = (unsigned char*)c->d_bf_ws;
     struct { uint8_t* p; } qrec{W + o_qrec}, amask{W + o_amask};
@@ -933,6 +987,11 @@ int hnswb200_bruteforce_topk_dev(hnswb200_ctx* c, const hnswb200_points* base, c
     HB_CUDA(cudaMemsetAsync(topk.p, 0xFF, nq * k * 8, c->stream));
     HB_CUDA(cudaMemsetAsync(tau.p, 0xFF, nq * 8, c->stream));
     HB_CUDA(cudaMemsetAsync(cnt.p, 0, nq * 4, c->stream));
+    if (base->metric == HNSWB200_METRIC_COSINE) {  // cosine: unit-norm copy of the queries first
+        float* qn = (float*)(W + o_qnorm);
+        HB_CUDA(launch_normalise(d_queries, nq, L.dim, qn, c->stream));
+        d_queries = qn;
+    }
     // queries are quantised like points (Point::new) and laid out as records
     HB_CUDA(launch_quantise(d_queries, nq, L, qrec.p, nullptr, nullptr, nullptr, nan_flag, c->stream));
     uint32_t flags[2] = {0, 0};

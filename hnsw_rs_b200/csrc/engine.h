@@ -42,6 +42,9 @@ struct hnswb200_ctx {
     uint64_t search_seq = 0;
     void* d_ws = nullptr;           // grow-only workspace for the host-buffer entry points
     size_t ws_bytes = 0;
+    void* d_norm_ws = nullptr;      // grow-only scratch for the normalised queries of a cosine index
+    size_t norm_ws_bytes = 0;
+    int norm_ws_reserve(size_t bytes);
     void* d_bf_ws = nullptr;        // grow-only scratch of the brute-force entry points (cudaMalloc per call costs more than the kernels)
     size_t bf_ws_bytes = 0;
     int bf_ws_reserve(size_t bytes);
@@ -58,6 +61,7 @@ struct hnswb200_points {
     uint64_t n = 0, cap = 0;
     uint8_t* d_rec = nullptr;
     std::vector<uint8_t> levels;  // Point.level (points/src/point.rs:8)
+    int metric = 0;               // HNSWB200_METRIC_*: cosine = rows and queries are L2-normalised on the device first
     int reserve(uint64_t want);   // grow device storage, keeps contents
 };
 

@@ -127,6 +127,28 @@ cudaError_t launch_unpack(const uint8_t* rec, uint64_t n, const RecLayout& L, ui
 }
 
 // ---------------------------------------------------------------------------
+// K0: L2-normalise rows (cosine as L2 over unit vectors: |a-b|^2 = 2 - 2 cos).  No reference analogue (the reference has
+// no cosine); arithmetic in the style of FullVec::distance: one strictly sequential f32 sum of squares,
+// correctly rounded sqrt and division.  A zero row stays zero.  In place is allowed.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) normalise_rows_kernel(const float* __restrict__ rows, uint64_t n, uint32_t dim, float* out) {
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const float* v = rows + r * dim;
+    float s = 0.0f;
+    for (uint32_t i = 0; i < dim; ++i) s = __fadd_rn(s, __fmul_rn(v[i], v[i]));
+    const float nrm = __fsqrt_rn(s);
+    float* o = out + r * dim;
+    for (uint32_t i = 0; i < dim; ++i) o[i] = nrm > 0.0f ? __fdiv_rn(v[i], nrm) : v[i];
+}
+
+cudaError_t launch_normalise(const float* rows, uint64_t n, uint32_t dim, float* out, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    normalise_rows_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(rows, n, dim, out);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
 // K2: batched distances
 // ---------------------------------------------------------------------------
 // one f32 query vs ids[n].  distance2point(point, idx) = point.dist2other(points[idx])

@@ -53,6 +53,8 @@ cudaError_t launch_pack(const uint8_t* codes, const float* mins, const float* de
                         const RecLayout& L, uint8_t* rec, cudaStream_t st);
 cudaError_t launch_unpack(const uint8_t* rec, uint64_t n, const RecLayout& L, uint8_t* codes,
                           float* mins, float* deltas, cudaStream_t st);
+// rows / |row| (cosine mode); out may alias rows
+cudaError_t launch_normalise(const float* rows, uint64_t n, uint32_t dim, float* out, cudaStream_t st);
 // distance2point / dist2many: one f32 query (quantised on device) against ids[n]
 cudaError_t launch_dist_query_many(const uint8_t* rec, const RecLayout& L, const float* query,
                                    const uint32_t* ids, uint64_t n, float* out, uint32_t* nan_flag,

@@ -20,14 +20,29 @@ from .points import SimplePoints
 
 
 class HNSW:
-    def __init__(self, m=12, ef_cons=None, dim=0, ctx=None, _handle=None):
+    METRICS = {"l2": 0, "cosine": 1}  # HNSWB200_METRIC_*
+
+    def __init__(self, m=12, ef_cons=None, dim=0, ctx=None, _handle=None, metric="l2"):
         self.ctx = ctx or Context.default()
         self._params0 = Params.from_m(m, dim) if ef_cons is None else Params.from_m_efcons(m, ef_cons, dim)
         self.h = _handle  # hnswb200_index*, created by the first insert_bulk / load
+        self._metric = self.METRICS[metric]
 
     @staticmethod
-    def new(m, ef_cons, dim, ctx=None):  # template.rs:133-144
-        return HNSW(m, ef_cons, dim, ctx)
+    def new(m, ef_cons, dim, ctx=None, metric="l2"):  # template.rs:133-144; metric="cosine" is an addition (unit-norm rows and queries)
+        return HNSW(m, ef_cons, dim, ctx, metric=metric)
+
+    @property
+    def metric(self):
+        code = int(lib().hnswb200_index_metric(self.h)) if self.h else self._metric
+        return "cosine" if code == 1 else "l2"
+
+    def set_metric(self, metric):
+        """Only while the index is empty; needed again after load() (the reference's save format has no metric field)."""
+        self._metric = self.METRICS[metric]
+        if self.h:
+            check(lib().hnswb200_index_set_metric(self.h, self._metric))
+        return self
 
     def __del__(self):
         if getattr(self, "h", None):
@@ -68,6 +83,13 @@ class HNSW:
                 raise HnswB200Error(_ffi.C.c_int(-1).value,
                                     f"The current index dimension is {prm.dim}, but tried inserting points of dimension {d}")
             h = _ffi.vp()
+            if self._metric:
+                # HNSW::new (empty index), choose the metric, then insert_bulk
+                check(lib().hnswb200_build(self.ctx.h, None, 0, d, C.byref(prm), None, b, C.byref(h)))
+                self.h = h
+                check(lib().hnswb200_index_set_metric(self.h, self._metric))
+                check(lib().hnswb200_index_insert_bulk(self.ctx.h, self.h, ptr(rows, _ffi.f32p), n, d, ptr(lv, _ffi.u8p), b))
+                return self
             check(lib().hnswb200_build(self.ctx.h, ptr(rows, _ffi.f32p), n, d, C.byref(prm), ptr(lv, _ffi.u8p), b,
                                        C.byref(h)))
             self.h = h

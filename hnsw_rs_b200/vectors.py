@@ -127,6 +127,17 @@ class QuantVec:
         return QuantVec(delta, mn, np.frombuffer(bytes(data[8:]), dtype=np.uint8).copy())
 
 
+def normalise_rows(rows, ctx=None):
+    """rows / |row| on the device (what a cosine index applies to rows and queries); a zero row stays zero."""
+    ctx = ctx or Context.default()
+    r = f32(rows)
+    if r.ndim != 2:
+        raise ValueError("rows must be n x dim")
+    out = np.empty_like(r)
+    check(lib().hnswb200_normalise(ctx.h, ptr(r, _ffi.f32p), r.shape[0], r.shape[1], ptr(out, _ffi.f32p)))
+    return out
+
+
 def quantise_rows(rows, ctx=None):
     """QuantVec::new for every row -> (codes[n,dim] u8, mins[n], deltas[n])."""
     ctx = ctx or Context.default()

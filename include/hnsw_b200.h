@@ -34,6 +34,13 @@ extern "C" {
 
 #define HNSWB200_NO_ID 0xFFFFFFFFu /* padding id in result arrays */
 
+/* Metric of a points object / index.  The reference only has Euclidean L2 (vectors/src/quant.rs:14-37); COSINE is an
+ * addition: every stored row and every query is L2-normalised on the device before it is quantised, and the reference's
+ * L2 path runs unchanged on the unit vectors (|a-b|^2 = 2 - 2 cos(a,b): the same ranking).  Reported distances are those
+ * L2 distances.  The metric is not part of the reference's save format: set it again after hnswb200_index_load_dir. */
+#define HNSWB200_METRIC_L2 0
+#define HNSWB200_METRIC_COSINE 1
+
 typedef struct hnswb200_ctx hnswb200_ctx;
 typedef struct hnswb200_points hnswb200_points;
 typedef struct hnswb200_graph hnswb200_graph;
@@ -73,6 +80,9 @@ void hnswb200_params_default(uint64_t m, int64_t ef_cons, uint64_t dim, hnswb200
 /* QuantVec::new for n rows (vectors/src/quant.rs:41-66). rows[n*dim] -> codes[n*dim], mins[n], deltas[n] */
 int hnswb200_quantise(hnswb200_ctx* ctx, const float* rows, uint64_t n, uint32_t dim, uint8_t* codes,
                       float* mins, float* deltas);
+/* rows[i] / |rows[i]| with a strictly sequential f32 sum of squares (the arithmetic style of FullVec::distance,
+ * vectors/src/full.rs:23-29); a zero row stays zero.  What a COSINE index applies to rows and queries. */
+int hnswb200_normalise(hnswb200_ctx* ctx, const float* rows, uint64_t n, uint32_t dim, float* out);
 /* FullVec::distance for n pairs of f32 vectors (vectors/src/full.rs:23-29): out[i] = d(x[i], y[i]) */
 int hnswb200_dist_full_pairs(hnswb200_ctx* ctx, const float* x, const float* y, uint64_t n, uint32_t dim,
                              float* out);
@@ -86,6 +96,9 @@ int hnswb200_points_from_f32(hnswb200_ctx* ctx, const float* rows, uint64_t n, u
                              const uint8_t* levels, hnswb200_points** out);
 int hnswb200_points_download(hnswb200_ctx* ctx, const hnswb200_points* p, uint8_t* codes, float* mins,
                              float* deltas, uint8_t* levels);
+/* HNSWB200_METRIC_*; may only change while the object holds no points */
+int hnswb200_points_set_metric(hnswb200_points* p, int metric);
+int hnswb200_points_metric(const hnswb200_points* p);
 uint64_t hnswb200_points_len(const hnswb200_points* p);
 uint32_t hnswb200_points_dim(const hnswb200_points* p);
 void hnswb200_points_destroy(hnswb200_points* p);
@@ -133,6 +146,8 @@ int hnswb200_index_save_dir(hnswb200_ctx* ctx, const hnswb200_index* ix, const c
 int hnswb200_index_load_dir(hnswb200_ctx* ctx, const char* dir, hnswb200_index** out);
 void hnswb200_index_destroy(hnswb200_index* ix);
 int hnswb200_index_params(const hnswb200_index* ix, hnswb200_params* out);
+int hnswb200_index_set_metric(hnswb200_index* ix, int metric); /* empty index only (after hnswb200_build with n = 0) */
+int hnswb200_index_metric(const hnswb200_index* ix);
 uint64_t hnswb200_index_len(const hnswb200_index* ix);                 /* HNSW::len */
 const hnswb200_points* hnswb200_index_points(const hnswb200_index* ix);
 const hnswb200_graph* hnswb200_index_graph(const hnswb200_index* ix);

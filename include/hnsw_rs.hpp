@@ -240,14 +240,21 @@ class HNSW {
    public:
     Params params;
 
-    // template.rs:133-144
-    static HNSW new_(size_t m, std::optional<size_t> ef_cons, size_t dim, Context& c = Context::global()) {
+    // template.rs:133-144.  metric: HNSWB200_METRIC_L2 (the reference) or HNSWB200_METRIC_COSINE (an addition: rows and
+    // queries are L2-normalised on the device, then the reference's L2 path runs on the unit vectors)
+    static HNSW new_(size_t m, std::optional<size_t> ef_cons, size_t dim, Context& c = Context::global(),
+                     int metric = HNSWB200_METRIC_L2) {
         hnswb200_params p;
         hnswb200_params_default(m, ef_cons ? (int64_t)*ef_cons : -1, dim, &p);
         hnswb200_index* ix = nullptr;
         check(hnswb200_build(c.get(), nullptr, 0, (uint32_t)dim, &p, nullptr, 0, &ix));
+        if (metric != HNSWB200_METRIC_L2) {
+            int rc = hnswb200_index_set_metric(ix, metric);
+            if (rc) { hnswb200_index_destroy(ix); check(rc); }
+        }
         return HNSW(&c, ix);
     }
+    int metric() const { return hnswb200_index_metric(ix_); }
     HNSW(HNSW&& o) noexcept : params(o.params), ctx_(o.ctx_), ix_(o.ix_) { o.ix_ = nullptr; }
     HNSW& operator=(HNSW&& o) noexcept {
         if (this != &o) {

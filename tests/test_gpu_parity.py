@@ -561,3 +561,38 @@ def test_search_pinned_host_buffers_are_used_in_place(H, oracle, glove, glove_in
         call()
     hq[3, 5] = 0.0
     call()  # the context recovers
+
+
+# ---- cosine (an addition: the reference has L2 only) ---------------------------------------------
+def test_cosine_index_is_l2_over_unit_rows(H, oracle):
+    """metric="cosine": rows and queries are L2-normalised on the device before they are quantised, then the reference's
+    L2 path runs unchanged.  (1) the normalisation matches numpy within 1e-6 relative; (2) a cosine index over raw rows
+    returns exactly what an L2 index returns over the device-normalised rows and queries, and that equals the oracle;
+    (3) the ranking is the cosine ranking: recall@10 against exact float cosine top-10 is high."""
+    r = np.random.default_rng(5)
+    base = (synth(5000, 100, 64, 31, normalise=False) * r.uniform(0.2, 5.0, (5000, 1))).astype(np.float32)
+    queries = (synth(200, 100, 64, 32, normalise=False) * r.uniform(0.2, 5.0, (200, 1))).astype(np.float32)
+    nb, nq = H.normalise_rows(base), H.normalise_rows(queries)
+    ref = base / np.linalg.norm(base.astype(np.float64), axis=1, keepdims=True)
+    assert np.allclose(nb, ref, rtol=1e-6, atol=1e-7)
+    assert np.array_equal(H.normalise_rows(np.zeros((2, 7), np.float32)), np.zeros((2, 7), np.float32))
+    cx = H.HNSW.new(16, 60, 100, metric="cosine").insert_bulk(base, batch=1)
+    lx = H.HNSW.new(16, 60, 100).insert_bulk(nb, batch=1)
+    assert cx.metric == "cosine" and lx.metric == "l2"
+    a = cx.ann_batch(queries, 10, 80, with_stats=True)
+    b = lx.ann_batch(nq, 10, 80, with_stats=True)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(bits(a[1]), bits(b[1])) and np.array_equal(a[3]["evals"], b[3]["evals"])
+    orc = oracle.Index(16, 60, 100).insert_bulk(nb)
+    o = orc.search_batch(nq, 10, 80)
+    assert np.array_equal(a[0], o[0]) and np.array_equal(bits(a[1]), bits(o[1]))
+    gt, _ = H.bruteforce_topk(cx._points(), queries, 10)          # normalises the queries itself
+    gt2, _ = H.bruteforce_topk(lx._points(), nq, 10)
+    assert np.array_equal(gt, gt2)
+    cos = (queries.astype(np.float64) / np.linalg.norm(queries, axis=1, keepdims=True)) @ ref.T
+    true10 = np.argsort(-cos, axis=1)[:, :10]
+    hits = sum(len(set(true10[i].tolist()) & set(a[0][i].tolist())) for i in range(len(queries)))
+    assert hits / true10.size > 0.9
+    d = cx._points().dist_query_many(queries[0], a[0][0])          # distances are L2 on the unit vectors: d^2 = 2 - 2 cos
+    assert np.allclose(d.astype(np.float64) ** 2, 2 - 2 * cos[0, a[0][0]], atol=2e-2)
+    with pytest.raises(H.HnswB200Error):
+        cx.set_metric("l2")                                          # rows are already quantised as unit vectors
