@@ -456,7 +456,10 @@ cudaError_t bf_tc_chunk(const uint8_t* base_rec, uint64_t n_base, const RecLayou
     uint32_t qsplit = 1;
     while (btiles * qsplit < (uint32_t)num_sms * 2 && qsplit * 2 <= nq_tiles) qsplit *= 2;
     const size_t smem = sizeof(TcSmem);
-    static bool attr = false;
+    static bool attr_d[64] = {};  // per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    bool& attr = attr_d[dev & 63];
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(bf_tc_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;

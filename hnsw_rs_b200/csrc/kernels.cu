@@ -519,8 +519,13 @@ template <class Q, class VIS, int KPL>
 static cudaError_t launch_search_reg_t(const SearchParams& p, int num_sms, cudaStream_t st, bool overlap_previous) {
     size_t smem = search_reg_warp_smem<VIS, Q, KPL>(p.tbits, p.qd_cap) * SEARCH_WPB;
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
-    static int occ_cache = 0;
-    static size_t occ_smem = 0;
+    // function attributes and occupancy are per device (a process may drive several GPUs)
+    static int occ_cache_d[64] = {};
+    static size_t occ_smem_d[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int& occ_cache = occ_cache_d[dev & 63];
+    size_t& occ_smem = occ_smem_d[dev & 63];
     cudaError_t e;
     if (occ_cache == 0 || occ_smem != smem) {
         e = cudaFuncSetAttribute(search_kernel_reg<Q, VIS, KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -556,8 +561,13 @@ template <class Q, class VIS, int KPL>
 static cudaError_t launch_search_t(const SearchParams& p, int num_sms, cudaStream_t st) {
     size_t smem = search_warp_smem<VIS>(p.kpl, p.tbits, p.qd_cap) * SEARCH_WPB;
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
-    static int occ_cache = 0;
-    static size_t occ_smem = 0;
+    // function attributes and occupancy are per device (a process may drive several GPUs)
+    static int occ_cache_d[64] = {};
+    static size_t occ_smem_d[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int& occ_cache = occ_cache_d[dev & 63];
+    size_t& occ_smem = occ_smem_d[dev & 63];
     cudaError_t e;
     if (occ_cache == 0 || occ_smem != smem) {
         e = cudaFuncSetAttribute(search_kernel<Q, VIS, KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
