@@ -596,3 +596,33 @@ def test_cosine_index_is_l2_over_unit_rows(H, oracle):
     assert np.allclose(d.astype(np.float64) ** 2, 2 - 2 * cos[0, a[0][0]], atol=2e-2)
     with pytest.raises(H.HnswB200Error):
         cx.set_metric("l2")                                          # rows are already quantised as unit vectors
+
+
+@pytest.mark.parametrize("dim,n,m,efc", [(100, 4000, 24, 60), (96, 3000, 40, 90), (50, 2500, 33, None)])
+def test_search_wide_rows(H, oracle, dim, n, m, efc):
+    """M > 16: adjacency rows wider than one 32-slot batch (layer 0: 2M slots, upper layers: M slots), on both list
+    implementations and through the device build."""
+    base = synth(n, dim, 48, 41)
+    queries = synth(150, dim, 48, 42)
+    orc = oracle.Index(m, efc, dim).insert_bulk(base)
+    for ef in (1, 30, 64, 100, 200, 300):
+        check_search(H, oracle, orc, queries, 10, ef)
+    ix = H.HNSW.new(m, efc, dim).insert_bulk(base, batch=1)
+    assert_same_graph([ix.export_layer(l) for l in range(ix.nb_layers())], orc.export_layers())
+
+
+def test_search_randomised_against_oracle(H, oracle):
+    """A small randomised sweep over dimension, M, ef_cons, ef and n (fixed seed): ids, distances, counts and counters
+    equal the oracle's on the oracle's graph, for every combination."""
+    r = np.random.default_rng(2024)
+    for trial in range(12):
+        dim = int(r.choice([3, 8, 17, 50, 64, 96, 100, 128, 130]))
+        m = int(r.integers(3, 21))
+        n = int(r.integers(300, 2500))
+        efc = None if r.random() < 0.3 else int(r.integers(m, 3 * m + 8))
+        base = synth(n, dim, 16, 100 + trial, normalise=bool(r.integers(0, 2)))
+        queries = synth(64, dim, 16, 200 + trial, normalise=False)
+        orc = oracle.Index(m, efc, dim).insert_bulk(base)
+        for ef in sorted(set(int(x) for x in r.integers(1, 280, 3))):
+            nres = int(r.choice([1, 10, 33]))
+            check_search(H, oracle, orc, queries, nres, ef)
