@@ -111,6 +111,8 @@ extern "C" {
     pub fn hnswb200_search(ctx: *mut hnswb200_ctx, ix: *const hnswb200_index, queries: *const f32, nq: u64, dim: u32,
                            n: u32, ef: u32, out_ids: *mut u32, out_dists: *mut f32, out_counts: *mut u32,
                            stats: *const hnswb200_search_stats) -> c_int;
+    pub fn hnswb200_search_async(ctx: *mut hnswb200_ctx, ix: *const hnswb200_index, queries: *const f32, nq: u64, dim: u32,
+                                 n: u32, ef: u32, out_ids: *mut u32, out_dists: *mut f32, out_counts: *mut u32) -> c_int;
     pub fn hnswb200_search_dev(ctx: *mut hnswb200_ctx, ix: *const hnswb200_index, d_queries: *const f32, nq: u64, n: u32,
                                ef: u32, d_out_ids: *mut u32, d_out_dists: *mut f32, d_out_counts: *mut u32,
                                d_hops: *mut u32, d_evals: *mut u32, d_flags: *mut u32, d_nbrs: *mut u32) -> c_int;

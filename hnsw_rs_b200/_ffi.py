@@ -85,6 +85,7 @@ SIGNATURES = {
     "hnswb200_index_graph": (vp, [vp]),
     "hnswb200_search": (C.c_int, [vp, vp, f32p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, u32p, f32p,
                                   u32p, C.POINTER(SearchStats)]),
+    "hnswb200_search_async": (C.c_int, [vp, vp, f32p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, u32p, f32p, u32p]),
     "hnswb200_search_dev": (C.c_int, [vp, vp, vp, C.c_uint64, C.c_uint32, C.c_uint32, vp, vp, vp, vp, vp, vp, vp]),
     "hnswb200_search_dev_gather": (C.c_int, [vp, vp, vp, C.c_uint64, C.c_uint32, C.c_uint32, vp, vp, vp, C.c_uint32,
                                              C.POINTER(vp), C.c_uint64]),

@@ -129,6 +129,10 @@ int hnswb200_ctx_sync(hnswb200_ctx* c) {
     if (!c) return fail(HNSWB200_EINVAL, "ctx is NULL");
     if (c->use()) return HNSWB200_ECUDA;
     HB_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->h_status && c->h_status[0]) {  // raised by an asynchronous search (hnswb200_search_async)
+        c->h_status[0] = 0;
+        return fail(HNSWB200_EINVAL, "search: NaN in a query (the reference panics in partial_cmp().unwrap())");
+    }
     return 0;
 }
 int hnswb200_ctx_device(const hnswb200_ctx* c) { return c ? c->device : -1; }
@@ -884,6 +888,36 @@ int hnswb200_ipc_close(hnswb200_ctx* c, void* p) {
     return 0;
 }
 
+// device alias of a page-locked (mapped) host buffer, or NULL for pageable memory
+static void* mapped_alias(const void* host) {
+    if (!host || getenv("HNSWB200_NO_ZERO_COPY")) return nullptr;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return (at.type == cudaMemoryTypeHost) ? at.devicePointer : nullptr;
+}
+
+int hnswb200_search_async(hnswb200_ctx* c, const hnswb200_index* ix, const float* queries, uint64_t nq, uint32_t dim,
+                          uint32_t n, uint32_t ef, uint32_t* out_ids, float* out_dists, uint32_t* out_counts) {
+    if (!c || !ix || (nq && (!queries || !out_ids))) return fail(HNSWB200_EINVAL, "search_async: NULL argument");
+    if (dim != ix->points->L.dim)
+        return fail(HNSWB200_EINVAL, "search: query dimension " + std::to_string(dim) + " != index dimension " +
+                                         std::to_string(ix->points->L.dim));
+    if (nq == 0) return 0;
+    int rc = search_check(ix, nq, n, ef);
+    if (rc) return rc;
+    if (c->use()) return HNSWB200_ECUDA;
+    void* dq = mapped_alias(queries);
+    void* di = mapped_alias(out_ids);
+    void* dd = out_dists ? mapped_alias(out_dists) : nullptr;
+    void* dc = out_counts ? mapped_alias(out_counts) : nullptr;
+    if (!dq || !di || (out_dists && !dd) || (out_counts && !dc))
+        return fail(HNSWB200_EINVAL, "search_async: every buffer must be page-locked (cudaHostAlloc / cudaHostRegister): "
+                                     "the kernel reads and writes them in place");
+    // no staging and no copies: the call only launches; consecutive calls overlap on the device
+    return search_dev_impl(c, ix, (const float*)dq, nq, n, ef, (uint32_t*)di, (float*)dd, (uint32_t*)dc, nullptr, nullptr,
+                           nullptr, nullptr, c->d_status);
+}
+
 int hnswb200_search(hnswb200_ctx* c, const hnswb200_index* ix, const float* queries, uint64_t nq,
                     uint32_t dim, uint32_t n, uint32_t ef, uint32_t* out_ids, float* out_dists,
                     uint32_t* out_counts, const hnswb200_search_stats* stats) {
@@ -901,12 +935,7 @@ int hnswb200_search(hnswb200_ctx* c, const hnswb200_index* ix, const float* quer
     // the steady-state path either way).
     const size_t b_q = nq * dim * 4, b_ids = nq * (size_t)n * 4, b_u = nq * 4;
     auto al = [](size_t v) { return (v + 255) / 256 * 256; };
-    auto mapped = [](const void* host) -> void* {
-        if (!host || getenv("HNSWB200_NO_ZERO_COPY")) return nullptr;
-        cudaPointerAttributes at;
-        if (cudaPointerGetAttributes(&at, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-        return (at.type == cudaMemoryTypeHost) ? at.devicePointer : nullptr;
-    };
+    auto mapped = [](const void* host) -> void* { return mapped_alias(host); };
     struct Buf { void* host; void* dev; size_t bytes; bool staged; };
     uint32_t* st_hops = stats ? stats->hops : nullptr;
     uint32_t* st_evals = stats ? stats->evals : nullptr;

@@ -158,6 +158,12 @@ const hnswb200_graph* hnswb200_index_graph(const hnswb200_index* ix);
 int hnswb200_search(hnswb200_ctx* ctx, const hnswb200_index* ix, const float* queries, uint64_t nq,
                     uint32_t dim, uint32_t n, uint32_t ef, uint32_t* out_ids, float* out_dists,
                     uint32_t* out_counts, const hnswb200_search_stats* stats);
+/* The host-buffer search without waiting: every buffer must be page-locked; the kernel reads the queries and writes
+ * the results in place over PCIe, the call only launches.  Consecutive calls overlap on the device.  Results (and a
+ * NaN-query error) are delivered by hnswb200_ctx_sync. */
+int hnswb200_search_async(hnswb200_ctx* ctx, const hnswb200_index* ix, const float* queries, uint64_t nq,
+                          uint32_t dim, uint32_t n, uint32_t ef, uint32_t* out_ids, float* out_dists,
+                          uint32_t* out_counts);
 /* same with device buffers, asynchronous on the context stream */
 int hnswb200_search_dev(hnswb200_ctx* ctx, const hnswb200_index* ix, const float* d_queries, uint64_t nq,
                         uint32_t n, uint32_t ef, uint32_t* d_out_ids, float* d_out_dists,

@@ -626,3 +626,36 @@ def test_search_randomised_against_oracle(H, oracle):
         for ef in sorted(set(int(x) for x in r.integers(1, 280, 3))):
             nres = int(r.choice([1, 10, 33]))
             check_search(H, oracle, orc, queries, nres, ef)
+
+
+def test_search_async_host_buffers(H, oracle, glove, glove_index):
+    """hnswb200_search_async: page-locked buffers, several batches in flight, one hnswb200_ctx_sync; pageable buffers are
+    refused; a NaN query surfaces at the sync."""
+    import ctypes as C
+    import torch
+    from hnsw_rs_b200 import _ffi
+    _, queries = glove
+    ix = to_gpu(H, glove_index)
+    nq, dim = queries.shape
+    ref = ix.ann_batch(queries, 10, 60)
+    lib = _ffi.lib()
+    hq = torch.from_numpy(queries.copy()).pin_memory()
+    outs = [(torch.zeros((nq, 10), dtype=torch.int32).pin_memory(), torch.zeros((nq, 10), dtype=torch.float32).pin_memory(),
+             torch.zeros(nq, dtype=torch.int32).pin_memory()) for _ in range(3)]
+    for i, d, c in outs:
+        _ffi.check(lib.hnswb200_search_async(ix.ctx.h, ix.h, C.cast(hq.data_ptr(), _ffi.f32p), nq, dim, 10, 60,
+                                             C.cast(i.data_ptr(), _ffi.u32p), C.cast(d.data_ptr(), _ffi.f32p),
+                                             C.cast(c.data_ptr(), _ffi.u32p)))
+    ix.ctx.sync()
+    for i, d, c in outs:
+        assert np.array_equal(i.numpy().view(np.uint32), ref[0]) and np.array_equal(bits(d.numpy()), bits(ref[1]))
+        assert np.array_equal(c.numpy().view(np.uint32), ref[2])
+    pageable = np.zeros((nq, 10), np.uint32)
+    assert lib.hnswb200_search_async(ix.ctx.h, ix.h, C.cast(hq.data_ptr(), _ffi.f32p), nq, dim, 10, 60,
+                                     pageable.ctypes.data_as(_ffi.u32p), None, None) == -1
+    hq[1, 0] = float("nan")
+    _ffi.check(lib.hnswb200_search_async(ix.ctx.h, ix.h, C.cast(hq.data_ptr(), _ffi.f32p), nq, dim, 10, 60,
+                                         C.cast(outs[0][0].data_ptr(), _ffi.u32p), None, None))
+    with pytest.raises(H.HnswB200Error):
+        ix.ctx.sync()
+    ix.ctx.sync()  # the status is cleared by the failing sync
