@@ -969,8 +969,10 @@ int hnswb200_search(hnswb200_ctx* c, const hnswb200_index* ix, const float* quer
     for (Buf& b : outs)
         if (b.staged) HB_CUDA(cudaMemcpyAsync(b.host, b.dev, b.bytes, cudaMemcpyDeviceToHost, c->stream));
     HB_CUDA(cudaStreamSynchronize(c->stream));
-    if (c->h_status[0])
+    if (c->h_status[0]) {
+        c->h_status[0] = 0;
         return fail(HNSWB200_EINVAL, "search: NaN in a query (the reference panics in partial_cmp().unwrap())");
+    }
     return 0;
 }
 
