@@ -27,19 +27,6 @@
 #pragma once
 #include "dist.cuh"
 
-#ifndef HB_SPEC_ROW
-#define HB_SPEC_ROW 1      // load the adjacency row of the next-best unexpanded entry one hop ahead
-#endif
-#ifndef HB_SPEC_RECORDS
-#define HB_SPEC_RECORDS 1  // also prefetch the records of that row's unvisited neighbours
-#endif
-#ifndef HB_PREFETCH_BATCH
-#define HB_PREFETCH_BATCH 1  // request all new records of a batch before the first round
-#endif
-#ifndef HB_PREFETCH_OVERTAKE
-#define HB_PREFETCH_OVERTAKE 1  // prefetch the row of a new entry that overtakes the speculated one
-#endif
-
 namespace hb {
 
 constexpr uint32_t EMPTY_ID = 0xFFFFFFFFu;
@@ -81,23 +68,9 @@ struct Vis32 {
         for (uint32_t i = lane; i < (1u << tbits) / 4; i += 32) p[i] = e;
         __syncwarp();
     }
-    // true if id was not yet in the set (and records it).  On an exhausted probe window the
-    // id is reported new but NOT recorded and *ovf is raised; the caller then falls back to
-    // a list-membership test so results stay exact.
-    __device__ __forceinline__ bool insert(uint32_t id, bool* ovf) const {
-        const uint32_t mask = (1u << tbits) - 1u;
-        uint32_t h = (id * 0x9E3779B1u) >> (32 - tbits);
-#pragma unroll 1
-        for (int probe = 0; probe < 48; ++probe) {
-            uint32_t old = atomicCAS(&tab[h], EMPTY_ID, id);
-            if (old == EMPTY_ID) return true;
-            if (old == id) return false;
-            h = (h + 1) & mask;
-        }
-        *ovf = true;
-        return true;
-    }
-    // warp-uniform form of insert (see Vis16::insert_warp)
+    // Insertion for all 32 lanes at once with warp-uniform control flow (want: this lane has an id to record);
+    // returns "id was new" per lane.  On an exhausted probe window the id is reported new but NOT recorded and
+    // *ovf is raised; the caller then falls back to a list-membership test so results stay exact.
     __device__ __forceinline__ bool insert_warp(uint32_t id, bool want, bool* ovf) const {
         const uint32_t mask = (1u << tbits) - 1u;
         uint32_t h = (id * 0x9E3779B1u) >> (32 - tbits);
@@ -118,19 +91,6 @@ struct Vis32 {
         }
         return isnew;
     }
-    // read-only membership test (used to filter speculative prefetches; "unknown" counts as absent)
-    __device__ __forceinline__ bool contains(uint32_t id) const {
-        const uint32_t mask = (1u << tbits) - 1u;
-        uint32_t h = (id * 0x9E3779B1u) >> (32 - tbits);
-#pragma unroll 1
-        for (int probe = 0; probe < 8; ++probe) {
-            uint32_t e = tab[h];
-            if (e == id) return true;
-            if (e == EMPTY_ID) return false;
-            h = (h + 1) & mask;
-        }
-        return false;
-    }
 };
 
 // 16-bit entries (ids < 2^B, table of T = 2^t entries): h = (id * odd) mod 2^B is a bijection
@@ -147,35 +107,11 @@ struct Vis16 {
         for (uint32_t i = lane; i < (1u << tbits) / 8; i += 32) p[i] = e;
         __syncwarp();
     }
-    __device__ __forceinline__ bool insert(uint32_t id, bool* ovf) const {
-        const uint32_t bmask = (bbits >= 32) ? 0xFFFFFFFFu : ((1u << bbits) - 1u);
-        const uint32_t h = (id * 0x9E3779B1u) & bmask;
-        const uint32_t rbits = bbits - tbits;
-        const uint32_t home = h >> rbits;
-        const uint32_t rem16 = (h & ((1u << rbits) - 1u)) << 4;
-        const uint32_t tmask = (1u << tbits) - 1u;
-#pragma unroll 1
-        for (uint32_t d = 0; d < 15; ++d) {
-            const uint32_t slot = (home + d) & tmask;
-            const uint32_t mine = rem16 | d;
-            uint32_t* wp = words + (slot >> 1);
-            const uint32_t sh = (slot & 1u) * 16u;
-            uint32_t w = *reinterpret_cast<volatile uint32_t*>(wp);
-            while (true) {
-                uint32_t e = (w >> sh) & 0xFFFFu;
-                if (e == mine) return false;
-                if (e != 0xFFFFu) break;  // occupied by another id: next displacement
-                uint32_t old = atomicCAS(wp, w, (w & ~(0xFFFFu << sh)) | (mine << sh));
-                if (old == w) return true;
-                w = old;  // the word changed under us: re-examine
-            }
-        }
-        *ovf = true;
-        return true;
-    }
-    // The same insertion for all 32 lanes at once with warp-uniform control flow (want: this lane has
-    // an id to record).  Every lane executes every iteration of the one loop, so the warp never
-    // splits into separately scheduled fragments.  Returns "id was new" per lane.
+    // Insertion for all 32 lanes at once with warp-uniform control flow (want: this lane has an id to
+    // record).  Every lane executes every iteration of the one loop, so the warp never splits into
+    // separately scheduled fragments (per-lane probe loops did: independent thread scheduling never
+    // re-joined them and every later collective ran once per fragment).  Returns "id was new" per lane;
+    // on an exhausted displacement window the id is reported new but not recorded and *ovf is raised.
     __device__ __forceinline__ bool insert_warp(uint32_t id, bool want, bool* ovf) const {
         // h = (id * odd) mod 2^B, kept top-aligned: the home slot is its top t bits, the remainder the next B-t
         const uint32_t h = (id * 0x9E3779B1u) << (32u - bbits);
@@ -204,22 +140,6 @@ struct Vis16 {
             pending = pending && !hit && !won && !full;
         }
         return isnew;
-    }
-    __device__ __forceinline__ bool contains(uint32_t id) const {
-        const uint32_t bmask = (bbits >= 32) ? 0xFFFFFFFFu : ((1u << bbits) - 1u);
-        const uint32_t h = (id * 0x9E3779B1u) & bmask;
-        const uint32_t rbits = bbits - tbits;
-        const uint32_t home = h >> rbits;
-        const uint32_t rem16 = (h & ((1u << rbits) - 1u)) << 4;
-        const uint32_t tmask = (1u << tbits) - 1u;
-        const unsigned short* t16 = reinterpret_cast<const unsigned short*>(words);
-#pragma unroll 1
-        for (uint32_t d = 0; d < 8; ++d) {
-            uint32_t e = t16[(home + d) & tmask];
-            if (e == (rem16 | d)) return true;
-            if (e == 0xFFFFu) return false;
-        }
-        return false;
     }
 };
 
@@ -357,33 +277,18 @@ __device__ __forceinline__ void search_layer(const Q& query, const uint8_t* __re
     }
     u64 worst = list[ef - 1] & KEY_MASK;  // masked sentinel (max) while |selected| < ef
     int cursor = 0;                       // every entry before `cursor` is expanded
-    // Speculation (memory-latency hiding only; the traversal itself is unchanged): while node c is
-    // expanded, the adjacency row of the next-best unexpanded entry c2 is loaded and the records of
-    // its not-yet-visited neighbours are prefetched into L2.  If c2 is indeed expanded next, its row
-    // is already in registers and its records are (nearly) resident.
-    const bool speculate = HB_SPEC_ROW && (layer == 0) && (g.S0 <= 32);
-    u64 spec_key = SENTINEL;
-    uint32_t spec_nb = EMPTY_ID;
     while (true) {
-        // candidates.pop_first(): first entry whose "expanded" bit is clear (and the one after it)
-        int found = -1, found2 = -1;
+        // candidates.pop_first(): first entry whose "expanded" bit is clear
+        int found = -1;
         for (int c = cursor; c < ef; c += 32) {
             int i = c + lane;
             bool un = (i < ef) && !(list[i] & EXP_FLAG);
             unsigned b = __ballot_sync(HB_FULL, un);
-            if (b) {
-                if (found < 0) {
-                    found = c + __ffs(b) - 1;
-                    b &= b - 1;
-                }
-                if (b) { found2 = c + __ffs(b) - 1; break; }
-                if (!speculate) break;
-            }
+            if (b) { found = c + __ffs(b) - 1; break; }
         }
         if (found < 0) break;
         cursor = found;
         const u64 ck = list[cursor];
-        const u64 ck2 = (speculate && found2 >= 0) ? list[found2] : SENTINEL;
         __syncwarp();
         if (lane == 0) list[cursor] = ck | EXP_FLAG;
         __syncwarp();
@@ -396,23 +301,12 @@ __device__ __forceinline__ void search_layer(const Q& query, const uint8_t* __re
         uint32_t S, row;
         if (layer == 0) { base = g.adj0; S = g.S0; row = cid; }
         else { base = g.upper_adj; S = g.SU; row = __ldg(g.upper_off + cid) + (layer - 1); }
-        const bool row_in_regs = speculate && (ck == spec_key);
-        uint32_t first_nb = spec_nb;
-        if (!row_in_regs) first_nb = ((uint32_t)lane < S) ? __ldg(base + (size_t)row * S + lane) : EMPTY_ID;
-        // start the next speculation: row of c2 (consumed one iteration later)
-        uint32_t nspec_nb = EMPTY_ID;
-        if (ck2 != SENTINEL) nspec_nb = ((uint32_t)lane < S) ? __ldg(base + (size_t)(uint32_t)ck2 * S + lane) : EMPTY_ID;
-        bool spec_prefetched = (ck2 == SENTINEL);
-        bool first_batch = true;
         while (row != EMPTY_ID) {
             const uint32_t* rp = base + (size_t)row * S;
             uint32_t next = EMPTY_ID;
             for (uint32_t b0 = 0; b0 < S; b0 += 32) {
                 uint32_t i = b0 + lane;
-                uint32_t nb;
-                if (first_batch) nb = first_nb;
-                else nb = (i < S) ? __ldg(rp + i) : EMPTY_ID;
-                first_batch = false;
+                uint32_t nb = (i < S) ? __ldg(rp + i) : EMPTY_ID;
                 bool marker = (nb != EMPTY_ID) && (nb & CHAIN_BIT);
                 unsigned mk = __ballot_sync(HB_FULL, marker);
                 if (mk) next = __shfl_sync(HB_FULL, nb, __ffs(mk) - 1) & ~CHAIN_BIT;
@@ -439,7 +333,7 @@ __device__ __forceinline__ void search_layer(const Q& query, const uint8_t* __re
                 }
                 // all records of this batch are requested at once (a second round does not pay
                 // a second memory latency)
-                if (HB_PREFETCH_BATCH && isnew) {
+                if (isnew) {
                     const uint8_t* rp8 = rec + (size_t)nb * rec_stride;
                     prefetch_l2(rp8);
                     if (rec_stride > 128) prefetch_l2(rp8 + 128);
@@ -456,16 +350,6 @@ __device__ __forceinline__ void search_layer(const Q& query, const uint8_t* __re
                     uint32_t cand = newbuf[act ? idx : 0];
                     // index.get_point(node).dist2other(point)  (searcher.rs:66-69)
                     float d = query.dist(rec + (size_t)cand * rec_stride, gl, gbase);
-                    if (HB_SPEC_RECORDS && !spec_prefetched) {
-                        // the speculative row has arrived by now (it was requested before these records)
-                        spec_prefetched = true;
-                        bool sv = (nspec_nb != EMPTY_ID) && !(nspec_nb & CHAIN_BIT) && !vis.contains(nspec_nb);
-                        if (sv) {
-                            const uint8_t* sp8 = rec + (size_t)nspec_nb * rec_stride;
-                            prefetch_l2(sp8);
-                            if (rec_stride > 128) prefetch_l2(sp8 + 128);
-                        }
-                    }
                     u64 key = make_key(d, cand);
                     // admission (searcher.rs:74-94): key < list[ef-1] covers |selected| < ef and strict <
                     bool want = act && gl == 0 && key < worst;
@@ -478,8 +362,6 @@ __device__ __forceinline__ void search_layer(const Q& query, const uint8_t* __re
                             int pos = L.insert(k, ef, lane);
                             minpos = min(minpos, pos);
                             worst = list[ef - 1] & KEY_MASK;
-                            // a new entry that overtakes c2 will be expanded first: fetch its row early
-                            if (HB_PREFETCH_OVERTAKE && speculate && lane == 0 && k < ck2) prefetch_l2(base + (size_t)(uint32_t)k * S);
                         }
                     }
                 }
@@ -487,16 +369,6 @@ __device__ __forceinline__ void search_layer(const Q& query, const uint8_t* __re
             }
             row = next;
         }
-        if (HB_SPEC_RECORDS && !spec_prefetched) {
-            bool sv = (nspec_nb != EMPTY_ID) && !(nspec_nb & CHAIN_BIT) && !vis.contains(nspec_nb);
-            if (sv) {
-                const uint8_t* sp8 = rec + (size_t)nspec_nb * rec_stride;
-                prefetch_l2(sp8);
-                if (rec_stride > 128) prefetch_l2(sp8 + 128);
-            }
-        }
-        spec_key = ck2;
-        spec_nb = nspec_nb;
         cursor = min(cursor, minpos);
     }
     // clear_candidates (searcher.rs:100): drop the expanded marks for the next layer
