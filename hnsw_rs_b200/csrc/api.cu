@@ -929,6 +929,9 @@ int hnswb200_search(hnswb200_ctx* c, const hnswb200_index* ix, const float* quer
     int rc = search_check(ix, nq, n, ef);
     if (rc) return rc;
     if (c->use()) return HNSWB200_ECUDA;
+    const bool prof_call = getenv("HNSWB200_PROFILE_CALL") != nullptr;
+    auto now_us = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3; };
+    const double t_enter = prof_call ? now_us() : 0;
     // Page-locked caller buffers are used in place: the kernel reads the queries and writes the results over
     // PCIe itself (88 + 4*dim bytes per query, spread over the whole launch), so there is no staging copy before
     // or after it.  Pageable buffers are staged through the grow-only per-context workspace (no cudaMalloc on
@@ -961,6 +964,7 @@ int hnswb200_search(hnswb200_ctx* c, const hnswb200_index* ix, const float* quer
     for (Buf& b : outs)
         if (b.host && !b.dev) { b.dev = w; w += al(b.bytes); b.staged = true; }
     c->h_status[0] = 0;
+    const double t_setup = prof_call ? now_us() : 0;
     if (q.staged) HB_CUDA(cudaMemcpyAsync(q.dev, queries, b_head, cudaMemcpyHostToDevice, c->stream));
     rc = search_dev_impl(c, ix, (const float*)q.dev, nq, n, ef, (uint32_t*)outs[0].dev, (float*)outs[1].dev,
                          (uint32_t*)outs[2].dev, (uint32_t*)outs[3].dev, (uint32_t*)outs[4].dev, (uint32_t*)outs[5].dev,
@@ -968,7 +972,13 @@ int hnswb200_search(hnswb200_ctx* c, const hnswb200_index* ix, const float* quer
     if (rc) return rc;
     for (Buf& b : outs)
         if (b.staged) HB_CUDA(cudaMemcpyAsync(b.host, b.dev, b.bytes, cudaMemcpyDeviceToHost, c->stream));
+    const double t_enq = prof_call ? now_us() : 0;
     HB_CUDA(cudaStreamSynchronize(c->stream));
+    if (prof_call) {
+        const double t_done = now_us();
+        fprintf(stderr, "[hnswb200 search] nq=%llu setup %.1f us, enqueue %.1f us, wait %.1f us\n", (unsigned long long)nq,
+                t_setup - t_enter, t_enq - t_setup, t_done - t_enq);
+    }
     if (c->h_status[0]) {
         c->h_status[0] = 0;
         return fail(HNSWB200_EINVAL, "search: NaN in a query (the reference panics in partial_cmp().unwrap())");

@@ -659,3 +659,40 @@ def test_search_async_host_buffers(H, oracle, glove, glove_index):
     with pytest.raises(H.HnswB200Error):
         ix.ctx.sync()
     ix.ctx.sync()  # the status is cleared by the failing sync
+
+
+def test_two_contexts_search_one_index_concurrently(H, oracle, glove, glove_index):
+    """One context per host thread: two threads with their own contexts (streams, workspaces) search the
+    same device-resident index at the same time; both get the oracle's answers."""
+    import ctypes as C
+    import threading
+    from hnsw_rs_b200 import _ffi
+    _, queries = glove
+    ix = to_gpu(H, glove_index)
+    ref = glove_index.search_batch(queries, 10, 50)
+    lib = _ffi.lib()
+    results, errors = {}, []
+
+    def worker(name):
+        try:
+            ctx = H.Context(0)
+            q = np.ascontiguousarray(queries, np.float32)
+            for rep in range(20):
+                ids = np.zeros((len(q), 10), np.uint32)
+                d = np.zeros((len(q), 10), np.float32)
+                c = np.zeros(len(q), np.uint32)
+                _ffi.check(lib.hnswb200_search(ctx.h, ix.h, q.ctypes.data_as(_ffi.f32p), len(q), q.shape[1], 10, 50,
+                                               ids.ctypes.data_as(_ffi.u32p), d.ctypes.data_as(_ffi.f32p),
+                                               c.ctypes.data_as(_ffi.u32p), None))
+                if not (np.array_equal(ids, ref[0]) and np.array_equal(bits(d), bits(ref[1])) and np.array_equal(c, ref[2])):
+                    errors.append((name, rep))
+            ctx.close()
+        except Exception as e:  # noqa: BLE001
+            errors.append((name, repr(e)))
+
+    ts = [threading.Thread(target=worker, args=(i,)) for i in range(2)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors, errors
