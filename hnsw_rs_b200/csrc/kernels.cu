@@ -437,7 +437,7 @@ __host__ __device__ inline size_t search_reg_warp_smem(uint32_t tbits, uint32_t 
 #endif
 constexpr int reg_min_blocks(int kpl) { return kpl <= 2 ? HB_REG_MINB2 : kpl <= 4 ? 5 : 4; }
 
-template <class Q, class VIS, int KPL>
+template <class Q, class VIS, int KPL, bool STATS>
 __global__ void __launch_bounds__(SEARCH_WPB * 32, reg_min_blocks(KPL)) search_kernel_reg(SearchParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -488,7 +488,7 @@ __global__ void __launch_bounds__(SEARCH_WPB * 32, reg_min_blocks(KPL)) search_k
         SearchCounters cnt{0u, 0u, 0u, 0u};
         RegList<KPL> L;
         __syncwarp();  // every lane has copied its part of qd before the merge buffer may overwrite it
-        search_query_reg<Q, VIS, KPL>(q, p.rec, p.L.stride, p.g, p.n_layers, p.ep, L, vis, newbuf, kbuf, mbuf, (int)p.ef, lane, cnt);
+        search_query_reg<Q, VIS, KPL, STATS>(q, p.rec, p.L.stride, p.g, p.n_layers, p.ep, L, vis, newbuf, kbuf, mbuf, (int)p.ef, lane, cnt);
         // get_top_selected(n)   (results.rs:59-61): position lane*KPL + s
         uint32_t mine = 0;
 #pragma unroll
@@ -515,8 +515,8 @@ __global__ void __launch_bounds__(SEARCH_WPB * 32, reg_min_blocks(KPL)) search_k
     }
 }
 
-template <class Q, class VIS, int KPL>
-static cudaError_t launch_search_reg_t(const SearchParams& p, int num_sms, cudaStream_t st, bool overlap_previous) {
+template <class Q, class VIS, int KPL, bool STATS>
+static cudaError_t launch_search_reg_s(const SearchParams& p, int num_sms, cudaStream_t st, bool overlap_previous) {
     size_t smem = search_reg_warp_smem<VIS, Q, KPL>(p.tbits, p.qd_cap) * SEARCH_WPB;
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
     // function attributes and occupancy are per device (a process may drive several GPUs)
@@ -528,10 +528,10 @@ static cudaError_t launch_search_reg_t(const SearchParams& p, int num_sms, cudaS
     size_t& occ_smem = occ_smem_d[dev & 63];
     cudaError_t e;
     if (occ_cache == 0 || occ_smem != smem) {
-        e = cudaFuncSetAttribute(search_kernel_reg<Q, VIS, KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(search_kernel_reg<Q, VIS, KPL, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         int occ = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, search_kernel_reg<Q, VIS, KPL>, SEARCH_WPB * 32, smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, search_kernel_reg<Q, VIS, KPL, STATS>, SEARCH_WPB * 32, smem);
         if (e != cudaSuccess) return e;
         occ_cache = occ < 1 ? 1 : occ;
         occ_smem = smem;
@@ -554,7 +554,7 @@ static cudaError_t launch_search_reg_t(const SearchParams& p, int num_sms, cudaS
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = overlap_previous ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, search_kernel_reg<Q, VIS, KPL>, p);
+    return cudaLaunchKernelEx(&cfg, search_kernel_reg<Q, VIS, KPL, STATS>, p);
 }
 
 template <class Q, class VIS, int KPL>
@@ -583,6 +583,15 @@ static cudaError_t launch_search_t(const SearchParams& p, int num_sms, cudaStrea
     int grid = (int)(want < cap ? want : cap);
     search_kernel<Q, VIS, KPL><<<grid, SEARCH_WPB * 32, smem, st>>>(p);
     return cudaGetLastError();
+}
+
+// the counters (hops, evaluations, neighbour ids, overflow flag) are optional outputs: a caller that asks for none of
+// them runs the variant that does not keep them
+template <class Q, class VIS, int KPL>
+static cudaError_t launch_search_reg_t(const SearchParams& p, int num_sms, cudaStream_t st, bool overlap_previous) {
+    if (p.out_hops || p.out_evals || p.out_flags || p.out_nbrs)
+        return launch_search_reg_s<Q, VIS, KPL, true>(p, num_sms, st, overlap_previous);
+    return launch_search_reg_s<Q, VIS, KPL, false>(p, num_sms, st, overlap_previous);
 }
 
 // visited-table geometry shared by the query and the build kernels

@@ -135,7 +135,7 @@ struct RegList {
 
 // One whole query.  On exit L holds the <= ef nearest evaluated nodes of layer 0, sorted.
 // Layers n_layers-1 .. 1 are searched with ef = 1 (template.rs:322-324), layer 0 with ef (:326).
-template <class Q, class VIS, int KPL>
+template <class Q, class VIS, int KPL, bool STATS>
 __device__ __forceinline__ void search_query_reg(const Q& query, const uint8_t* __restrict__ rec,
                                                  uint32_t rec_stride, const GraphView& g, uint32_t n_layers,
                                                  uint32_t ep, RegList<KPL>& L, const VIS& vis,
@@ -172,7 +172,7 @@ __device__ __forceinline__ void search_query_reg(const Q& query, const uint8_t* 
         bool isnew = vis.insert_warp(nb, valid, &ovf);
         if (__any_sync(HB_FULL, ovf)) {
             // rare: probe window exhausted.  Exactness is kept by testing list membership.
-            cnt.overflow = 1;
+            if (STATS) cnt.overflow = 1;
             unsigned om = __ballot_sync(HB_FULL, ovf);
 #pragma unroll 1
             while (om) {
@@ -186,7 +186,7 @@ __device__ __forceinline__ void search_query_reg(const Q& query, const uint8_t* 
         const unsigned nm = __ballot_sync(HB_FULL, isnew);
         const int ncnt = __popc(nm);
         if (ncnt) {
-            cnt.evals += ncnt;
+            if (STATS) cnt.evals += ncnt;
             if (isnew) {
                 const int my = __popc(nm & ((1u << lane) - 1));
                 newbuf[my] = nb;
@@ -247,7 +247,7 @@ __device__ __forceinline__ void search_query_reg(const Q& query, const uint8_t* 
                 seed = true;
                 continue;
             }
-            cnt.hops++;
+            if (STATS) cnt.hops++;
             // layer.neighbors_vec(cid)  (graph/src/graph.rs:103-113) as fixed-stride rows
             const uint32_t cid = rkey_id(ck);
             row = layer ? __ldg(g.upper_off + cid) + (layer - 1) : cid;
@@ -259,7 +259,7 @@ __device__ __forceinline__ void search_query_reg(const Q& query, const uint8_t* 
             const bool ok = !(nb & CHAIN_BIT);
             const unsigned mk = __ballot_sync(HB_FULL, !ok && nb != EMPTY_ID);
             if (mk) next = __shfl_sync(HB_FULL, nb, __ffs(mk) - 1) & ~CHAIN_BIT;
-            cnt.nbrs += __popc(__ballot_sync(HB_FULL, ok));
+            if (STATS) cnt.nbrs += __popc(__ballot_sync(HB_FULL, ok));
         }
     }
 }

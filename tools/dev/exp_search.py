@@ -73,10 +73,12 @@ def main():
     d_nb = torch.empty(nq, dtype=torch.int32, device="cuda")
     rec = 8 + a.dim
     for ef in [int(x) for x in a.efs.split(",")]:
-        def run():
+        def run(stats=not os.environ.get("EXP_NO_STATS")):
             _ffi.check(_ffi.lib().hnswb200_search_dev(ctx.h, ix.h, dq.data_ptr(), nq, 10, ef, d_ids.data_ptr(),
-                                                      d_d.data_ptr(), d_cnt.data_ptr(), d_h.data_ptr(),
-                                                      d_e.data_ptr(), d_f.data_ptr(), d_nb.data_ptr()))
+                                                      d_d.data_ptr(), d_cnt.data_ptr(), d_h.data_ptr() if stats else None,
+                                                      d_e.data_ptr() if stats else None, d_f.data_ptr() if stats else None,
+                                                      d_nb.data_ptr() if stats else None))
+        run(True)
         for _ in range(3):
             run()
         torch.cuda.synchronize()
