@@ -399,7 +399,7 @@ def main():
         traffic = json.load(open(os.path.join(ROOT, "profiles", "search_kernel_traffic.json"))).get("dram_bytes_per_launch")
     except Exception:
         pass
-    kname = ("hb::search_kernel_reg<RegQuery<12,4>,Vis16,%d>" % (2 if ef <= 64 else 4 if ef <= 128 else 8)) if ef <= 256 \
+    kname = ("hb::search_kernel_reg<RegQuery<12,4>,Vis16,%d,false>" % (2 if ef <= 64 else 4 if ef <= 128 else 8)) if ef <= 256 \
         else "hb::search_kernel<RegQuery<12,4>,Vis16,0>"
     roofline = {"bound": "hbm", "kernel": kname, "achieved": round(achieved, 1),
                 "peak": peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
