@@ -11,6 +11,7 @@
 #include <sys/stat.h>
 
 #include <algorithm>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -436,12 +437,11 @@ bool materialise_row(const hb::AdjStore& s, uint32_t row, uint64_t chain_base, u
                      uint64_t& chain_used, std::unordered_map<uint32_t, std::vector<uint32_t>>& chains,
                      RowSink& sink) {
     const uint32_t S = s.S, d = s.deg[row];
-    std::vector<uint32_t> slots(S, hb::H_EMPTY);
-    if (d <= S) {
-        for (uint32_t i = 0; i < d; ++i) slots[i] = s.get(row, i);
-        sink.put(row, slots.data());
+    if (d <= S) {  // the host row is already in device form (unused slots are EMPTY)
+        sink.put(row, &s.data[(size_t)row * S]);
         return true;
     }
+    std::vector<uint32_t> slots(S, hb::H_EMPTY);
     std::vector<uint32_t>& ch = chains[row];
     uint32_t i = 0;
     uint64_t cur = row;
@@ -492,10 +492,18 @@ int hnswb200_graph::upload_full() {
     chain0_used = chainu_used = 0;
     const uint64_t n = h.n_points();
     // leave head-room so appended points / new continuation rows do not force a rebuild
+    // continuation rows: twice what the rows wider than S need now (a row keeps the ones it was given)
+    auto chain_rows = [](const hb::AdjStore& s) {
+        uint64_t c = 0;
+        for (uint32_t d : s.deg)
+            if (d > s.S) c += (d - 2) / (s.S - 1);
+        return c;
+    };
     rows0_cap = n + n / 8 + 1024;
-    chain0_cap = std::max<uint64_t>(1024, h.a0.spill.size() * 2 + n / 256);
+    chain0_cap = std::max<uint64_t>(1024, chain_rows(h.a0) * 2 + n / 64);
     rowsu_cap = h.au.rows() + h.au.rows() / 8 + 1024;
-    chainu_cap = std::max<uint64_t>(1024, h.au.spill.size() * 2 + h.au.rows() / 256);
+    chainu_cap = std::max<uint64_t>(1024, chain_rows(h.au) * 2 + h.au.rows() / 64);
+    ++n_full_uploads;
     upper_off_cap = rows0_cap;
     const uint32_t S0 = h.a0.S, SU = h.au.S;
     std::vector<uint32_t> st0((rows0_cap + chain0_cap) * S0, hb::H_EMPTY);
@@ -546,9 +554,11 @@ int hnswb200_graph::upload_rows(std::vector<uint32_t>& dirty0, std::vector<uint3
         return upload_full();
     }
     if (ctx->use()) return HNSWB200_ECUDA;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     for (int which = 0; which < 2; ++which) {
         std::vector<uint32_t>& dirty = which ? dirtyu : dirty0;
         if (dirty.empty()) continue;
+        const double ts0 = now();
         const hb::AdjStore& s = which ? h.au : h.a0;
         const uint32_t S = s.S;
         // de-duplicate with a mark array (the list holds every touched row, often many times)
@@ -559,8 +569,10 @@ int hnswb200_graph::upload_rows(std::vector<uint32_t>& dirty0, std::vector<uint3
             if (!mark[r]) { mark[r] = 1; dirty[uniq++] = r; }
         dirty.resize(uniq);
         for (uint32_t r : dirty) mark[r] = 0;
+        const double ta = now();
+        t_up[0] += ta - ts0;
         // stage: rows whose degree fits are already in device form on the host
-        size_t need = uniq + 64;
+        size_t need = 2 * uniq + 64;  // a row wider than S is staged as head + continuation row(s)
         const uint32_t Smax = std::max(h.a0.S, h.au.S);
         if (stage_cap < need || stage_S < Smax) {
             if (h_stage_rows) cudaFreeHost(h_stage_rows);
@@ -575,9 +587,17 @@ int hnswb200_graph::upload_rows(std::vector<uint32_t>& dirty0, std::vector<uint3
             HB_CUDA(cudaMalloc((void**)&d_stage_rows, stage_cap * 4));
             HB_CUDA(cudaMalloc((void**)&d_stage_data, stage_cap * (size_t)stage_S * 4));
         }
+        const double tb = now();
+        t_up[1] += tb - ta;
         size_t cnt = 0;
         std::vector<uint32_t> big;  // rows that need continuation rows: rare
-        for (uint32_t r : dirty) {
+        for (size_t di = 0; di < dirty.size(); ++di) {
+            const uint32_t r = dirty[di];
+            if (di + 8 < dirty.size()) {  // the rows are scattered over the whole store: fetch ahead
+                const char* nx = (const char*)&s.data[(size_t)dirty[di + 8] * S];
+                for (uint32_t b = 0; b < S * 4; b += 64) __builtin_prefetch(nx + b);
+                __builtin_prefetch(&s.deg[dirty[di + 8]]);
+            }
             if (s.deg[r] <= S) {
                 h_stage_rows[cnt] = r;
                 memcpy(h_stage_data + cnt * S, &s.data[(size_t)r * S], (size_t)S * 4);
@@ -586,6 +606,10 @@ int hnswb200_graph::upload_rows(std::vector<uint32_t>& dirty0, std::vector<uint3
                 big.push_back(r);
             }
         }
+        const double tc = now();
+        t_up[2] += tc - tb;
+        n_up_rows += cnt;
+        n_up_big += big.size();
         if (!big.empty()) {
             std::vector<uint32_t> rows, data;
             ListSink sink(rows, data, S);
@@ -598,7 +622,7 @@ int hnswb200_graph::upload_rows(std::vector<uint32_t>& dirty0, std::vector<uint3
                     return upload_full();
                 }
             }
-            if (cnt + rows.size() > stage_cap) {  // cannot happen with the +64 slack unless many chains
+            if (cnt + rows.size() > stage_cap) {  // only with rows wider than 2S-1
                 dirty0.clear();
                 dirtyu.clear();
                 return upload_full();
@@ -609,10 +633,13 @@ int hnswb200_graph::upload_rows(std::vector<uint32_t>& dirty0, std::vector<uint3
                 ++cnt;
             }
         }
+        const double ts1 = now();
         HB_CUDA(cudaMemcpyAsync(d_stage_rows, h_stage_rows, cnt * 4, cudaMemcpyHostToDevice, ctx->stream));
         HB_CUDA(cudaMemcpyAsync(d_stage_data, h_stage_data, cnt * (size_t)S * 4, cudaMemcpyHostToDevice, ctx->stream));
         HB_CUDA(hb::launch_scatter_rows(which ? d_adju : d_adj0, S, d_stage_rows, d_stage_data, (uint32_t)cnt, ctx->stream));
         HB_CUDA(cudaStreamSynchronize(ctx->stream));
+        t_stage += ts1 - ts0;
+        t_xfer += now() - ts1;
         dirty.clear();
     }
     return 0;

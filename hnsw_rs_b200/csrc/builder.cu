@@ -23,6 +23,7 @@
 #include <chrono>
 #include <vector>
 
+#include "commit.h"
 #include "engine.h"
 #include "search.cuh"
 
@@ -386,105 +387,6 @@ void draw_levels(uint64_t m, uint64_t n, uint8_t* out) {
     }
 }
 
-// ---------------------------------------------------------------------------
-// host commit of one point's insertion results (template.rs:196-251)
-// ---------------------------------------------------------------------------
-struct LayerSel {
-    uint32_t layer;
-    std::vector<uint32_t> ids;
-    std::vector<float> dists;
-};
-
-struct CommitScratch {
-    struct Prune { uint32_t layer, node, kept_off, kept_n, drop_off, drop_n; };
-    std::vector<Prune> prunes;
-    std::vector<uint32_t> kept_ids, drop_ids, lost;
-    std::vector<float> kept_w;
-    std::vector<std::pair<u64, uint32_t>> keyed;
-};
-
-static int commit_point(HostGraph& h, uint32_t pid, const std::vector<LayerSel>& res,
-                        std::vector<uint32_t>& dirty0, std::vector<uint32_t>& dirtyu, CommitScratch& cs) {
-    // make_connections: every layer first (ascending layer, ascending Dist)
-    for (const LayerSel& ls : res) {
-        std::vector<uint32_t>* dirty = ls.layer == 0 ? &dirty0 : &dirtyu;
-        for (size_t i = 0; i < ls.ids.size(); ++i) {
-            int r = h.add_edge(ls.layer, pid, ls.ids[i], ls.dists[i], dirty);
-            if (r) { set_error("make_connections: add_edge failed (self connection or node not in graph)"); return HNSWB200_ESTATE; }
-        }
-    }
-    // prune_connections: for every new neighbour x above the layer cap keep the cap nearest
-    // (select_simple, template.rs:614-621).  All results are computed before any is applied.
-    cs.prunes.clear();
-    cs.kept_ids.clear();
-    cs.kept_w.clear();
-    cs.drop_ids.clear();
-    for (const LayerSel& ls : res) {
-        const AdjStore& s = h.store(ls.layer);
-        const uint32_t cap = h.cap(ls.layer);
-        for (uint32_t x : ls.ids) {
-            uint32_t row = h.row(x, ls.layer);
-            uint32_t d = s.deg[row];
-            if (!(d > cap)) continue;
-            // (prune_results is a map keyed by node; a node occurs once in one point's selection)
-            cs.keyed.clear();
-            for (uint32_t i = 0; i < d; ++i) {
-                float w = s.getw(row, i);
-                uint32_t bits;
-                memcpy(&bits, &w, 4);
-                cs.keyed.push_back({((u64)bits << 32) | s.get(row, i), i});
-            }
-            // keep the `cap` smallest (dist, id) keys; almost always d == cap + 1
-            std::nth_element(cs.keyed.begin(), cs.keyed.begin() + cap, cs.keyed.end());
-            CommitScratch::Prune pr;
-            pr.layer = ls.layer;
-            pr.node = x;
-            pr.kept_off = (uint32_t)cs.kept_ids.size();
-            pr.kept_n = cap;
-            pr.drop_off = (uint32_t)cs.drop_ids.size();
-            pr.drop_n = d - cap;
-            for (uint32_t i = 0; i < d; ++i) {
-                if (i < cap) {
-                    cs.kept_ids.push_back((uint32_t)cs.keyed[i].first);
-                    cs.kept_w.push_back(s.getw(row, cs.keyed[i].second));
-                } else {
-                    cs.drop_ids.push_back((uint32_t)cs.keyed[i].first);
-                }
-            }
-            cs.prunes.push_back(pr);
-        }
-    }
-    // make_pruned_connections: ascending layer, ascending node id (oracle convention for the
-    // reference's hash-map iteration order).  replace_neighbors(x, kept) = isolate_node(x) +
-    // add_neighbors(x, kept) (graph.rs:85-94,128-148): members of `kept` are removed and re-added
-    // (no net change), the others lose the edge unless their degree is 1.  A kept edge has to be
-    // re-created only if an earlier replacement of this same point cut it, i.e. x lost an edge.
-    std::sort(cs.prunes.begin(), cs.prunes.end(), [](const CommitScratch::Prune& a, const CommitScratch::Prune& b) {
-        return a.layer != b.layer ? a.layer < b.layer : a.node < b.node;
-    });
-    cs.lost.clear();
-    uint32_t lost_layer = 0xFFFFFFFFu;
-    for (const CommitScratch::Prune& pr : cs.prunes) {
-        std::vector<uint32_t>* dirty = pr.layer == 0 ? &dirty0 : &dirtyu;
-        if (pr.layer != lost_layer) { cs.lost.clear(); lost_layer = pr.layer; }
-        const bool x_lost = std::find(cs.lost.begin(), cs.lost.end(), pr.node) != cs.lost.end();
-        for (uint32_t i = 0; i < pr.drop_n; ++i) {
-            uint32_t nb = cs.drop_ids[pr.drop_off + i];
-            if (h.store(pr.layer).find(h.row(pr.node, pr.layer), nb) < 0) continue;  // already cut earlier
-            if (h.degree(nb, pr.layer) == 1) continue;
-            h.remove_edge(pr.layer, pr.node, nb, dirty);
-            cs.lost.push_back(nb);
-        }
-        if (x_lost) {
-            for (uint32_t i = 0; i < pr.kept_n; ++i) {
-                int r = h.add_edge(pr.layer, pr.node, cs.kept_ids[pr.kept_off + i], cs.kept_w[pr.kept_off + i], dirty);
-                if (r) { set_error("make_pruned_connections: replace_neighbors failed"); return HNSWB200_ESTATE; }
-            }
-        }
-    }
-    return 0;
-}
-
 // edge lengths for a graph that was imported without them
 static int ensure_weights(hnswb200_ctx* c, hnswb200_index* ix) {
     HostGraph& h = ix->graph->h;
@@ -580,8 +482,11 @@ int build_insert(hnswb200_ctx* c, hnswb200_index* ix, const std::vector<uint32_t
     p.out_cnt = d_ocnt.p;
     p.out_evals = d_oev.p;
     p.work_counter = c->d_scratch;
-    std::vector<uint32_t> o_ids((size_t)maxb * nl * m), o_cnt((size_t)maxb * nl);
-    std::vector<float> o_d((size_t)maxb * nl * m);
+    PinBuf<uint32_t> o_ids, o_cnt;  // page-locked: the copies back run at link speed and do not block the host
+    PinBuf<float> o_d;
+    HB_CUDA(o_ids.alloc((size_t)maxb * nl * m));
+    HB_CUDA(o_cnt.alloc((size_t)maxb * nl));
+    HB_CUDA(o_d.alloc((size_t)maxb * nl * m));
     std::vector<uint8_t> jl(maxb);
 
     int grid_cap = 0;
@@ -635,22 +540,39 @@ int build_insert(hnswb200_ctx* c, hnswb200_index* ix, const std::vector<uint32_t
         HB_CUDA(cudaMemcpyAsync(o_cnt.data(), d_ocnt.p, (size_t)nb * nl * 4, cudaMemcpyDeviceToHost, c->stream));
         HB_CUDA(cudaStreamSynchronize(c->stream));
         double t1 = now();
+        // the commit is a chain of dependent cache misses on the rows of the selected neighbours:
+        // touch the rows of a job a few jobs ahead of the one being committed
+        auto touch_rows = [&](uint32_t j) {
+            for (uint32_t l = 0; l < nl; ++l) {
+                uint32_t cnt = o_cnt[(size_t)j * nl + l];
+                if (cnt == 0) continue;
+                const AdjStore& s = h.store(l);
+                const uint32_t* oi = &o_ids[((size_t)j * nl + l) * m];
+                for (uint32_t i = 0; i < cnt; ++i) {
+                    uint32_t row = h.row(oi[i], l);
+                    const char* a = (const char*)&s.data[(size_t)row * s.S];
+                    const char* w = (const char*)&s.w[(size_t)row * s.S];
+                    for (uint32_t b = 0; b < s.S * 4; b += 64) {
+                        __builtin_prefetch(a + b, 1);
+                        __builtin_prefetch(w + b, 1);
+                    }
+                    __builtin_prefetch(&s.deg[row], 1);
+                }
+            }
+        };
+        constexpr uint32_t COMMIT_AHEAD = 4;
+        for (uint32_t j = 0; j < std::min(COMMIT_AHEAD, nb); ++j) touch_rows(j);
         for (uint32_t j = 0; j < nb; ++j) {
+            if (j + COMMIT_AHEAD < nb) touch_rows(j + COMMIT_AHEAD);
             uint32_t pid = order[pos + j];
             res.clear();
             for (uint32_t l = 0; l < nl; ++l) {
                 uint32_t cnt = o_cnt[(size_t)j * nl + l];
                 if (cnt == 0) continue;
-                LayerSel ls;
-                ls.layer = l;
-                const uint32_t* oi = &o_ids[((size_t)j * nl + l) * m];
-                const float* od = &o_d[((size_t)j * nl + l) * m];
-                ls.ids.assign(oi, oi + cnt);
-                ls.dists.assign(od, od + cnt);
-                res.push_back(std::move(ls));
+                res.push_back(LayerSel{l, cnt, &o_ids[((size_t)j * nl + l) * m], &o_d[((size_t)j * nl + l) * m]});
             }
-            rc = commit_point(h, pid, res, d0, du, cs);
-            if (rc) return rc;
+            const char* cerr = nullptr;
+            if (commit_point(h, pid, res, d0, du, cs, &cerr)) return (set_error(cerr), HNSWB200_ESTATE);
         }
         double t2 = now();
         rc = G->upload_rows(d0, du);
@@ -661,8 +583,8 @@ int build_insert(hnswb200_ctx* c, hnswb200_index* ix, const std::vector<uint32_t
         t_kernel += t1 - t0; t_commit += t2 - t1; t_upload += t3 - t2;
     }
     if (prof)
-        fprintf(stderr, "[hnswb200 build] points=%zu batches=%llu kernel+copy=%.3fs commit=%.3fs upload=%.3fs smem/block=%zu grid_cap=%d\n",
-                order.size(), (unsigned long long)n_batches, t_kernel, t_commit, t_upload, smem, grid_cap);
+        fprintf(stderr, "[hnswb200 build] points=%zu batches=%llu kernel+copy=%.3fs commit=%.3fs upload=%.3fs (stage %.3fs = dedupe %.3f + alloc %.3f + gather %.3f + wide rows; %llu rows, %llu wide; transfer %.3fs, %llu full uploads) smem/block=%zu grid_cap=%d\n",
+                order.size(), (unsigned long long)n_batches, t_kernel, t_commit, t_upload, G->t_stage, G->t_up[0], G->t_up[1], G->t_up[2], (unsigned long long)G->n_up_rows, (unsigned long long)G->n_up_big, G->t_xfer, (unsigned long long)G->n_full_uploads, smem, grid_cap);
     return 0;
 }
 

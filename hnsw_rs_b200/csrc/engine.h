@@ -20,6 +20,15 @@ struct DevBuf {  // scoped device buffer
     ~DevBuf() { if (p) cudaFree(p); }
     cudaError_t alloc(size_t n) { return cudaMalloc((void**)&p, (n ? n : 1) * sizeof(T)); }
 };
+template <typename T>
+struct PinBuf {  // scoped page-locked host buffer
+    T* p = nullptr;
+    ~PinBuf() { if (p) cudaFreeHost(p); }
+    cudaError_t alloc(size_t n) { return cudaHostAlloc((void**)&p, (n ? n : 1) * sizeof(T), cudaHostAllocDefault); }
+    T& operator[](size_t i) { return p[i]; }
+    const T& operator[](size_t i) const { return p[i]; }
+    T* data() { return p; }
+};
 }  // namespace hb
 
 #define HB_CUDA(call)                                              \
@@ -82,6 +91,9 @@ struct hnswb200_graph {
     size_t stage_cap = 0;
     uint32_t stage_S = 0;
     std::vector<uint8_t> mark0, marku;
+    uint64_t n_full_uploads = 0, n_up_rows = 0, n_up_big = 0;
+    double t_up[3] = {0, 0, 0};  // de-duplicate / staging allocation / row gather
+    double t_stage = 0, t_xfer = 0;  // upload_rows: host gather into the staging buffer / copy + scatter + wait (build profile)
     hb::DevGraph view() const;
     int upload_full();                                        // (re)build the device mirror
     int upload_rows(std::vector<uint32_t>& dirty0, std::vector<uint32_t>& dirtyu);  // touched rows only

@@ -7,6 +7,9 @@
 // only the touched rows to the device.
 #pragma once
 #include <stdint.h>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 #include <algorithm>
 #include <unordered_map>
@@ -16,7 +19,9 @@ namespace hb {
 
 constexpr uint32_t H_EMPTY = 0xFFFFFFFFu;
 
-// neighbour sets with set semantics; S inline slots per row, rare overflow in `spill`.
+// neighbour sets with set semantics; S inline slots per row, one more slot per row in `xdata`
+// (a full row holds cap + 1 neighbours between make_connections and prune_connections, which
+// is the steady state of the build), rare overflow beyond that in `spill`.
 // Every edge also carries its length d(a,b) (bit-identical in both directions, since
 // (x-y)^2 is exactly symmetric): the build's prune step (hnsw/src/template.rs:209-238)
 // needs d(x, n) for every neighbour n of x, and all of those were already produced by
@@ -27,7 +32,9 @@ struct AdjStore {
     std::vector<uint32_t> data;
     std::vector<float> w;
     std::vector<uint32_t> deg;
-    std::unordered_map<uint32_t, std::vector<uint32_t>> spill;
+    std::vector<uint32_t> xdata;  // slot S of every row
+    std::vector<float> xw;
+    std::unordered_map<uint32_t, std::vector<uint32_t>> spill;  // slots S+1...
     std::unordered_map<uint32_t, std::vector<float>> wspill;
 
     void init(uint32_t cap_) {
@@ -40,41 +47,61 @@ struct AdjStore {
         data.resize(data.size() + n * S, H_EMPTY);
         w.resize(w.size() + n * S, 0.0f);
         deg.resize(deg.size() + n, 0);
+        xdata.resize(xdata.size() + n, H_EMPTY);
+        xw.resize(xw.size() + n, 0.0f);
     }
     uint32_t get(uint32_t row, uint32_t i) const {
         if (i < S) return data[(size_t)row * S + i];
-        return spill.find(row)->second[i - S];
+        if (i == S) return xdata[row];
+        return spill.find(row)->second[i - S - 1];
     }
     float getw(uint32_t row, uint32_t i) const {
         if (i < S) return w[(size_t)row * S + i];
-        return wspill.find(row)->second[i - S];
+        if (i == S) return xw[row];
+        return wspill.find(row)->second[i - S - 1];
     }
     void set(uint32_t row, uint32_t i, uint32_t v, float wt) {
         if (i < S) {
             data[(size_t)row * S + i] = v;
             w[(size_t)row * S + i] = wt;
+        } else if (i == S) {
+            xdata[row] = v;
+            xw[row] = wt;
         } else {
             auto& sp = spill[row];
             auto& ws = wspill[row];
-            if (sp.size() <= i - S) { sp.resize(i - S + 1); ws.resize(i - S + 1); }
-            sp[i - S] = v;
-            ws[i - S] = wt;
+            if (sp.size() <= i - S - 1) { sp.resize(i - S); ws.resize(i - S); }
+            sp[i - S - 1] = v;
+            ws[i - S - 1] = wt;
         }
     }
     void setw(uint32_t row, uint32_t i, float wt) {
         if (i < S) w[(size_t)row * S + i] = wt;
-        else wspill[row][i - S] = wt;
+        else if (i == S) xw[row] = wt;
+        else wspill[row][i - S - 1] = wt;
     }
     int find(uint32_t row, uint32_t v) const {
         uint32_t d = deg[row];
         const uint32_t* p = &data[(size_t)row * S];
         uint32_t lim = d < S ? d : S;
+#if defined(__SSE2__)
+        // S is a multiple of 4 and unused slots hold H_EMPTY (never a node id): compare whole quads
+        const __m128i vv = _mm_set1_epi32((int)v);
+        for (uint32_t i = 0; i < lim; i += 4) {
+            int hit = _mm_movemask_ps(_mm_castsi128_ps(_mm_cmpeq_epi32(_mm_loadu_si128((const __m128i*)(p + i)), vv)));
+            if (hit) return (int)(i + (uint32_t)__builtin_ctz((unsigned)hit));
+        }
+#else
         for (uint32_t i = 0; i < lim; ++i)
             if (p[i] == v) return (int)i;
+#endif
         if (d > S) {
-            const auto& sp = spill.find(row)->second;
-            for (uint32_t i = 0; i < d - S; ++i)
-                if (sp[i] == v) return (int)(S + i);
+            if (xdata[row] == v) return (int)S;
+            if (d > S + 1) {
+                const auto& sp = spill.find(row)->second;
+                for (uint32_t i = 0; i < d - S - 1; ++i)
+                    if (sp[i] == v) return (int)(S + 1 + i);
+            }
         }
         return -1;
     }
@@ -90,6 +117,7 @@ struct AdjStore {
         uint32_t last = deg[row] - 1;
         set(row, (uint32_t)i, get(row, last), getw(row, last));
         if (last < S) data[(size_t)row * S + last] = H_EMPTY;
+        else if (last == S) xdata[row] = H_EMPTY;
         else {
             auto it = spill.find(row);
             it->second.pop_back();

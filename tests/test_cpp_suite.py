@@ -36,3 +36,11 @@ def test_cpp_reference_suite_passes():
     print(r.stdout)
     assert r.returncode == 0, r.stdout[-2000:]
     assert "12 passed; 0 failed" in r.stdout
+
+
+def test_host_edge_store_matches_set_semantics():
+    """hostgraph.h (the build's host-side Graph: add_edge / remove_edge / replace_neighbors, graph.rs:37-148) against
+    std::set / std::map at degrees below, at and far above the row width; host only."""
+    _build()
+    r = subprocess.run([os.path.join(ROOT, "tests", "cpp", "hostgraph_test")], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "all checks passed" in r.stdout, r.stdout[-2000:]
