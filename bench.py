@@ -45,55 +45,103 @@ def synth(n, dim, ncent, seed, sigma=0.35):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md's clocks line).  The timed region of a
+    default run is only some tens of milliseconds, far shorter than nvidia-smi's start-up, so the samples come from an
+    NVML polling thread (pynvml: the same counters nvidia-smi prints) that is already running when the region starts;
+    only the samples whose time stamps fall inside [mark_begin, mark_end] are reported.  nvidia-smi -lms is the fallback."""
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
-        self.rows = []
-        self.p = None
+        self.rows = []      # (t, sm_mhz, reasons bit mask)
+        self.max_mhz = None
+        self.stop_flag = False
+        self.t0 = self.t1 = None
+        self.kind = None
+        self.t = None
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            uuid = "GPU-" + str(torch.cuda.get_device_properties(self.gpu).uuid)
+            return pynvml, pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+        except Exception:
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.gpu]) if vis and vis.split(",")[self.gpu].strip().isdigit() else self.gpu
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(idx)
 
     def start(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
-                                       "--format=csv,noheader,nounits", "-lms", "100"],
-                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.p = None
+            nv, h = self._nvml_handle()
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            bits = [nv.nvmlClocksThrottleReasonHwSlowdown, nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                    nv.nvmlClocksThrottleReasonSwThermalSlowdown, nv.nvmlClocksThrottleReasonSwPowerCap]
 
-    def _read(self):
-        for line in self.p.stdout:
-            self.rows.append(line.strip())
+            def poll():
+                while not self.stop_flag:
+                    try:
+                        mhz = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                        r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                        self.rows.append((time.perf_counter(), mhz, sum(1 << i for i, b in enumerate(bits) if r & b)))
+                    except Exception:
+                        pass
+                    time.sleep(0.0005)
+            self.kind = "nvml"
+            self.t = threading.Thread(target=poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            pass
+        try:
+            q = ("index,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}",
+                                       "--format=csv,noheader,nounits", "-lms", "20"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+
+            def read():
+                for line in self.p.stdout:
+                    f = [x.strip() for x in line.split(",")]
+                    try:
+                        self.max_mhz = float(f[2])
+                        self.rows.append((time.perf_counter(), float(f[1]),
+                                          sum(1 << i for i, v in enumerate(f[3:7]) if v.lower().startswith("active"))))
+                    except (ValueError, IndexError):
+                        continue
+            self.kind = "nvidia-smi"
+            self.t = threading.Thread(target=read, daemon=True)
+            self.t.start()
+            time.sleep(0.5)  # nvidia-smi needs a moment before its first line
+        except Exception:
+            self.kind = None
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
-        if not self.p:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=2)
-        except Exception:
-            self.p.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            f = [x.strip() for x in r.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        if not self.kind:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["no NVML and no nvidia-smi"]}
+        self.stop_flag = True
+        if self.kind == "nvidia-smi":
+            self.p.terminate()
+        self.t.join(timeout=2)
+        inside = [r for r in self.rows if self.t0 is not None and self.t0 <= r[0] <= (self.t1 or r[0])]
+        near = inside
+        if not near and self.rows and self.t0 is not None:
+            # a region shorter than one polling period: the samples bracketing it
+            mid = 0.5 * (self.t0 + (self.t1 or self.t0))
+            near = sorted(self.rows, key=lambda r: abs(r[0] - mid))[:2]
+        mask = 0
+        for r in near:
+            mask |= r[2]
+        return {"sm_mhz": float(np.median([r[1] for r in near])) if near else None, "sm_max_mhz": self.max_mhz,
+                "samples": len(inside), "samples_total": len(self.rows), "source": self.kind,
+                "window": "samples taken between the first launch of the timed region and its final synchronize",
+                "reasons": [n for i, n in enumerate(self.NAMES) if mask >> i & 1]}
 
 
 def recall_at_k(ids, gt):
@@ -111,9 +159,12 @@ def alg_bytes(hops, nbrs, evals, nq, dim, k):
 
 def oracle_from_index(ix):
     from oracle import pyoracle as O
-    codes, mins, deltas, levels = ix._points().download()
     p = ix.params
     layers = [ix.export_layer(l) for l in range(ix.nb_layers())]
+    if ix.vec_type == "full":
+        vals, levels = ix._points().values()
+        return O.Index.from_parts(p.m, p.ef_cons, p.dim, p.ep, vals, None, None, levels, layers)
+    codes, mins, deltas, levels = ix._points().download()
     return O.Index.from_parts(p.m, p.ef_cons, p.dim, p.ep, codes, mins, deltas, levels, layers)
 
 
@@ -262,6 +313,9 @@ def main():
         return run_reference(a, ix, queries, gt, ef, rec, cfg)
 
     # ---------------- device-resident throughput (value) ----------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()  # already polling during the warm-up, so the timed region is covered from its first launch
     for _ in range(a.warmup):
         search_dev(ef)
     torch.cuda.synchronize()
@@ -274,10 +328,8 @@ def main():
         dist.all_gather_into_tensor(reference_gather, d_ids)  # NCCL, outside the timed region: the checker of the fused path
         dist.barrier()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.mark_begin()
     e0.record()
     for s in range(a.steps):
         # consecutive searches are programmatic dependent launches: the blocks of step s+1 take over the SMs
@@ -288,6 +340,7 @@ def main():
             search_dev(ef)
     e1.record()
     torch.cuda.synchronize()
+    sampler.mark_end()
     if world > 1:
         dist.barrier()
     total_ms = e0.elapsed_time(e1)

@@ -14,6 +14,8 @@ pub const HNSWB200_ESTATE: c_int = -5;
 pub const HNSWB200_NO_ID: u32 = 0xFFFF_FFFF;
 pub const HNSWB200_METRIC_L2: c_int = 0;
 pub const HNSWB200_METRIC_COSINE: c_int = 1;
+pub const HNSWB200_VEC_QUANT: c_int = 0;
+pub const HNSWB200_VEC_FULL: c_int = 1;
 
 #[repr(C)] pub struct hnswb200_ctx { _p: [u8; 0] }
 #[repr(C)] pub struct hnswb200_points { _p: [u8; 0] }
@@ -50,6 +52,9 @@ extern "C" {
     pub fn hnswb200_ctx_set_stream(ctx: *mut hnswb200_ctx, cuda_stream: *mut c_void) -> c_int;
     pub fn hnswb200_ctx_sync(ctx: *mut hnswb200_ctx) -> c_int;
     pub fn hnswb200_ctx_device(ctx: *const hnswb200_ctx) -> c_int;
+    // `type VecType` (points/src/point.rs:4) as a property of the context: HNSWB200_VEC_QUANT (0) / HNSWB200_VEC_FULL (1)
+    pub fn hnswb200_ctx_set_vec_type(ctx: *mut hnswb200_ctx, vec_type: c_int) -> c_int;
+    pub fn hnswb200_ctx_vec_type(ctx: *const hnswb200_ctx) -> c_int;
 
     pub fn hnswb200_params_default(m: u64, ef_cons: i64, dim: u64, out: *mut hnswb200_params);
 
@@ -71,6 +76,10 @@ extern "C" {
                                     out: *mut *mut hnswb200_points) -> c_int;
     pub fn hnswb200_points_download(ctx: *mut hnswb200_ctx, p: *const hnswb200_points, codes: *mut u8, mins: *mut f32,
                                     deltas: *mut f32, levels: *mut u8) -> c_int;
+    pub fn hnswb200_points_upload_f32(ctx: *mut hnswb200_ctx, rows: *const f32, levels: *const u8, n: u64, dim: u32,
+                                      out: *mut *mut hnswb200_points) -> c_int;
+    pub fn hnswb200_points_values(ctx: *mut hnswb200_ctx, p: *const hnswb200_points, rows: *mut f32, levels: *mut u8) -> c_int;
+    pub fn hnswb200_points_vec_type(p: *const hnswb200_points) -> c_int;
     pub fn hnswb200_points_len(p: *const hnswb200_points) -> u64;
     pub fn hnswb200_points_dim(p: *const hnswb200_points) -> u32;
     pub fn hnswb200_points_destroy(p: *mut hnswb200_points);

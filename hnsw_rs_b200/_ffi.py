@@ -47,6 +47,8 @@ SIGNATURES = {
     "hnswb200_ctx_set_stream": (C.c_int, [vp, vp]),
     "hnswb200_ctx_sync": (C.c_int, [vp]),
     "hnswb200_ctx_device": (C.c_int, [vp]),
+    "hnswb200_ctx_set_vec_type": (C.c_int, [vp, C.c_int]),
+    "hnswb200_ctx_vec_type": (C.c_int, [vp]),
     "hnswb200_params_default": (None, [C.c_uint64, C.c_int64, C.c_uint64, C.POINTER(Params)]),
     "hnswb200_quantise": (C.c_int, [vp, f32p, C.c_uint64, C.c_uint32, u8p, f32p, f32p]),
     "hnswb200_normalise": (C.c_int, [vp, f32p, C.c_uint64, C.c_uint32, f32p]),
@@ -58,6 +60,9 @@ SIGNATURES = {
     "hnswb200_points_upload": (C.c_int, [vp, u8p, f32p, f32p, u8p, C.c_uint64, C.c_uint32, C.POINTER(vp)]),
     "hnswb200_points_from_f32": (C.c_int, [vp, f32p, C.c_uint64, C.c_uint32, u8p, C.POINTER(vp)]),
     "hnswb200_points_download": (C.c_int, [vp, vp, u8p, f32p, f32p, u8p]),
+    "hnswb200_points_upload_f32": (C.c_int, [vp, f32p, u8p, C.c_uint64, C.c_uint32, C.POINTER(vp)]),
+    "hnswb200_points_values": (C.c_int, [vp, vp, f32p, u8p]),
+    "hnswb200_points_vec_type": (C.c_int, [vp]),
     "hnswb200_points_len": (C.c_uint64, [vp]),
     "hnswb200_points_dim": (C.c_uint32, [vp]),
     "hnswb200_points_destroy": (None, [vp]),

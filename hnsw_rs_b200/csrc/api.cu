@@ -138,6 +138,16 @@ int hnswb200_ctx_sync(hnswb200_ctx* c) {
 }
 int hnswb200_ctx_device(const hnswb200_ctx* c) { return c ? c->device : -1; }
 
+// `type VecType = QuantVec;` (points/src/point.rs:4) as a property of the context: every point set created through it
+// afterwards (points_from_f32, build, insert) stores that vector type.  Existing point sets keep theirs.
+int hnswb200_ctx_set_vec_type(hnswb200_ctx* c, int vec_type) {
+    if (!c) return fail(HNSWB200_EINVAL, "ctx is NULL");
+    if (vec_type != HNSWB200_VEC_QUANT && vec_type != HNSWB200_VEC_FULL) return fail(HNSWB200_EINVAL, "unknown vector type");
+    c->vec_type = vec_type;
+    return 0;
+}
+int hnswb200_ctx_vec_type(const hnswb200_ctx* c) { return c ? c->vec_type : -1; }
+
 void hnswb200_params_default(uint64_t m, int64_t ef_cons, uint64_t dim, hnswb200_params* p) {
     p->ep = 0;
     p->m = m;
@@ -237,12 +247,13 @@ int hnswb200_points::reserve(uint64_t want) {
     return 0;
 }
 
-static int points_new(hnswb200_ctx* c, uint32_t dim, uint64_t n, hnswb200_points** out) {
+static int points_new(hnswb200_ctx* c, uint32_t dim, uint64_t n, hnswb200_points** out, int vec_type = -1) {
     if (dim == 0) return fail(HNSWB200_EINVAL, "points: dimension 0");
     if (n >= (1ull << 31)) return fail(HNSWB200_EINVAL, "points: more than 2^31-1 points");
     hnswb200_points* p = new hnswb200_points();
     p->ctx = c;
-    p->L = hb_make_layout(dim);
+    if (vec_type < 0) vec_type = c->vec_type;
+    p->L = hb_make_layout_kind(dim, vec_type == HNSWB200_VEC_FULL ? HB_REC_F32 : HB_REC_QUANT);
     int rc = p->reserve(n);
     if (rc) { delete p; return rc; }
     *out = p;
@@ -265,13 +276,19 @@ int hb::points_append_f32(hnswb200_ctx* c, hnswb200_points* p, const float* rows
         uint64_t cnt = std::min(CH, n - s);
         HB_CUDA(cudaMemcpyAsync(d_rows.p, rows + s * p->L.dim, cnt * p->L.dim * 4, cudaMemcpyHostToDevice, c->stream));
         if (p->metric == HNSWB200_METRIC_COSINE) HB_CUDA(launch_normalise(d_rows.p, cnt, p->L.dim, d_rows.p, c->stream));
-        HB_CUDA(launch_quantise(d_rows.p, cnt, p->L, p->d_rec + (p->n + s) * p->L.stride, nullptr, nullptr,
-                                nullptr, nan_flag, c->stream));
+        if (p->L.kind == HB_REC_F32)
+            HB_CUDA(launch_pack_f32(d_rows.p, cnt, p->L, p->d_rec + (p->n + s) * p->L.stride, nan_flag, c->stream));
+        else
+            HB_CUDA(launch_quantise(d_rows.p, cnt, p->L, p->d_rec + (p->n + s) * p->L.stride, nullptr, nullptr,
+                                    nullptr, nan_flag, c->stream));
     }
     uint32_t flag = 0;
     HB_CUDA(cudaMemcpyAsync(&flag, nan_flag, 4, cudaMemcpyDeviceToHost, c->stream));
     HB_CUDA(cudaStreamSynchronize(c->stream));
-    if (flag) return fail(HNSWB200_EINVAL, "NaN in vector (the reference panics in partial_cmp().unwrap())");
+    if (flag)
+        return fail(HNSWB200_EINVAL, p->L.kind == HB_REC_F32
+                                         ? "non-finite value in vector (a NaN distance makes the reference panic in partial_cmp().unwrap())"
+                                         : "NaN in vector (the reference panics in partial_cmp().unwrap())");
     for (uint64_t i = 0; i < n; ++i) p->levels.push_back(levels ? levels[i] : 0);
     p->n += n;
     return 0;
@@ -284,7 +301,7 @@ int hnswb200_points_upload(hnswb200_ctx* c, const uint8_t* codes, const float* m
     if (!c || !out || (n && (!codes || !mins || !deltas))) return fail(HNSWB200_EINVAL, "points_upload: NULL argument");
     if (c->use()) return HNSWB200_ECUDA;
     hnswb200_points* p = nullptr;
-    int rc = points_new(c, dim, n, &p);
+    int rc = points_new(c, dim, n, &p, HNSWB200_VEC_QUANT);  // codes, min, delta: a QuantVec set whatever the context's type
     if (rc) return rc;
     if (n) {
         DevBuf<uint8_t> d_codes;
@@ -326,6 +343,8 @@ int hnswb200_points_download(hnswb200_ctx* c, const hnswb200_points* p, uint8_t*
     uint64_t n = p->n;
     if (levels && n) memcpy(levels, p->levels.data(), n);
     if (n == 0 || (!codes && !mins && !deltas)) return 0;
+    if (p->L.kind != HB_REC_QUANT)
+        return fail(HNSWB200_ESTATE, "points_download: these points store f32 vectors (FullVec); use hnswb200_points_values");
     DevBuf<uint8_t> d_codes;
     DevBuf<float> d_mins, d_deltas;
     HB_CUDA(d_codes.alloc(n * p->L.dim));
@@ -339,6 +358,36 @@ int hnswb200_points_download(hnswb200_ctx* c, const hnswb200_points* p, uint8_t*
     return 0;
 }
 
+int hnswb200_points_upload_f32(hnswb200_ctx* c, const float* rows, const uint8_t* levels, uint64_t n, uint32_t dim,
+                               hnswb200_points** out) {
+    if (!c || !out || (n && !rows)) return fail(HNSWB200_EINVAL, "points_upload_f32: NULL argument");
+    if (c->use()) return HNSWB200_ECUDA;
+    hnswb200_points* p = nullptr;
+    int rc = points_new(c, dim, n, &p, HNSWB200_VEC_FULL);
+    if (rc) return rc;
+    rc = points_append_f32(c, p, rows, n, levels);
+    if (rc) { hnswb200_points_destroy(p); return rc; }
+    *out = p;
+    return 0;
+}
+
+int hnswb200_points_values(hnswb200_ctx* c, const hnswb200_points* p, float* rows, uint8_t* levels) {
+    if (!c || !p) return fail(HNSWB200_EINVAL, "points_values: NULL argument");
+    if (c->use()) return HNSWB200_ECUDA;
+    const uint64_t n = p->n;
+    if (levels && n) memcpy(levels, p->levels.data(), n);
+    if (n == 0 || !rows) return 0;
+    DevBuf<float> d_rows;
+    HB_CUDA(d_rows.alloc(n * p->L.dim));
+    HB_CUDA(launch_record_values(p->d_rec, n, p->L, d_rows.p, c->stream));
+    HB_CUDA(cudaMemcpyAsync(rows, d_rows.p, n * p->L.dim * 4, cudaMemcpyDeviceToHost, c->stream));
+    HB_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int hnswb200_points_vec_type(const hnswb200_points* p) {
+    return p ? (p->L.kind == HB_REC_F32 ? HNSWB200_VEC_FULL : HNSWB200_VEC_QUANT) : -1;
+}
 uint64_t hnswb200_points_len(const hnswb200_points* p) { return p ? p->n : 0; }
 uint32_t hnswb200_points_dim(const hnswb200_points* p) { return p ? p->L.dim : 0; }
 void hnswb200_points_destroy(hnswb200_points* p) {
@@ -1060,12 +1109,13 @@ int hnswb200_bruteforce_topk_dev(hnswb200_ctx* c, const hnswb200_points* base, c
         HB_CUDA(launch_normalise(d_queries, nq, L.dim, qn, c->stream));
         d_queries = qn;
     }
-    // queries are quantised like points (Point::new) and laid out as records
-    HB_CUDA(launch_quantise(d_queries, nq, L, qrec.p, nullptr, nullptr, nullptr, nan_flag, c->stream));
+    // queries become points like the stored ones (Point::new) and are laid out as records
+    if (L.kind == HB_REC_F32) HB_CUDA(launch_pack_f32(d_queries, nq, L, qrec.p, nan_flag, c->stream));
+    else HB_CUDA(launch_quantise(d_queries, nq, L, qrec.p, nullptr, nullptr, nullptr, nan_flag, c->stream));
     uint32_t flags[2] = {0, 0};
     HB_CUDA(cudaMemcpyAsync(flags, nan_flag, 8, cudaMemcpyDeviceToHost, c->stream));
     HB_CUDA(cudaStreamSynchronize(c->stream));
-    if (flags[0]) return fail(HNSWB200_EINVAL, "bruteforce: NaN in a query");
+    if (flags[0]) return fail(HNSWB200_EINVAL, L.kind == HB_REC_F32 ? "bruteforce: non-finite value in a query" : "bruteforce: NaN in a query");
     // Chunks double in size: with tau = current k-th best, the expected number of survivors of a
     // chunk as large as everything seen before is <= k per query.  A chunk that overflows the
     // per-query buffer (adversarial order) is redone in pieces of `cap` rows, which cannot overflow.
@@ -1212,20 +1262,36 @@ int hnswb200_index_save_dir(hnswb200_ctx* c, const hnswb200_index* ix, const cha
     if (n == 0) return fail(HNSWB200_ESTATE, "save: the index holds no points");
     std::string d(dir);
     if (mkdir(d.c_str(), 0777) != 0 && errno != EEXIST) return fail(HNSWB200_EIO, "Could not create dir " + d);
-    std::vector<uint8_t> codes(n * dim), levels(n);
-    std::vector<float> mins(n), deltas(n);
-    int rc = hnswb200_points_download(c, P, codes.data(), mins.data(), deltas.data(), levels.data());
-    if (rc) return rc;
-    // points file: points.rs:119-131, point.rs:55-61, quant.rs:102-110 (min before delta)
     std::vector<uint8_t> b;
-    b.reserve(16 + n * (9 + dim));
-    put_u64(b, n);
-    put_u64(b, 9 + dim);
-    for (uint64_t i = 0; i < n; ++i) {
-        b.push_back(levels[i]);
-        put_f32(b, mins[i]);
-        put_f32(b, deltas[i]);
-        b.insert(b.end(), &codes[i * dim], &codes[(i + 1) * dim]);
+    int rc;
+    if (P->L.kind == HB_REC_F32) {
+        // points file with VecType = FullVec: points.rs:119-131, point.rs:55-61, full.rs:55-61 (dim big-endian floats)
+        std::vector<uint8_t> levels(n);
+        std::vector<float> vals(n * dim);
+        rc = hnswb200_points_values(c, P, vals.data(), levels.data());
+        if (rc) return rc;
+        b.reserve(16 + n * (1 + 4 * dim));
+        put_u64(b, n);
+        put_u64(b, 1 + 4 * dim);
+        for (uint64_t i = 0; i < n; ++i) {
+            b.push_back(levels[i]);
+            for (uint64_t j = 0; j < dim; ++j) put_f32(b, vals[i * dim + j]);
+        }
+    } else {
+        std::vector<uint8_t> codes(n * dim), levels(n);
+        std::vector<float> mins(n), deltas(n);
+        rc = hnswb200_points_download(c, P, codes.data(), mins.data(), deltas.data(), levels.data());
+        if (rc) return rc;
+        // points file: points.rs:119-131, point.rs:55-61, quant.rs:102-110 (min before delta)
+        b.reserve(16 + n * (9 + dim));
+        put_u64(b, n);
+        put_u64(b, 9 + dim);
+        for (uint64_t i = 0; i < n; ++i) {
+            b.push_back(levels[i]);
+            put_f32(b, mins[i]);
+            put_f32(b, deltas[i]);
+            b.insert(b.end(), &codes[i * dim], &codes[(i + 1) * dim]);
+        }
     }
     if (!write_file(d + "/points", b)) return fail(HNSWB200_EIO, "Could not write bytes to point file");
     b.clear();  // params.rs:78-91
@@ -1269,23 +1335,40 @@ int hnswb200_index_load_dir(hnswb200_ctx* c, const char* dir, hnswb200_index** o
     std::vector<uint8_t> b;
     if (!read_file(d + "/points", b) || b.size() < 16) return fail(HNSWB200_EIO, "Problem reading points file");
     uint64_t n = get_u64(&b[0]), psz = get_u64(&b[8]);
-    if (psz < 10 || b.size() < 16 + n * psz) return fail(HNSWB200_EIO, "points file is truncated");
-    uint64_t dim = psz - 9;
-    std::vector<uint8_t> codes(n * dim), levels(n);
-    std::vector<float> mins(n), deltas(n);
-    for (uint64_t i = 0; i < n; ++i) {
-        const uint8_t* p = &b[16 + i * psz];
-        levels[i] = p[0];
-        mins[i] = get_f32(p + 1);
-        deltas[i] = get_f32(p + 5);
-        memcpy(&codes[i * dim], p + 9, dim);
-    }
+    if (psz < 5 || b.size() < 16 + n * psz) return fail(HNSWB200_EIO, "points file is truncated");
+    std::vector<uint8_t> pb;
+    pb.swap(b);
     if (!read_file(d + "/params", b) || b.size() < 52) return fail(HNSWB200_EIO, "Problem reading params file");
     hnswb200_params prm;
     prm.m = get_u64(&b[0]); prm.mmax = get_u64(&b[8]); prm.mmax0 = get_u64(&b[16]);
     prm.ml = get_f32(&b[24]);
     prm.ef_cons = get_u64(&b[28]); prm.dim = get_u64(&b[36]); prm.ep = (uint32_t)get_u64(&b[44]);
-    if (prm.dim != dim) return fail(HNSWB200_EIO, "params.dim does not match the point size");
+    // The file does not name its VecType; the point size does: 1 + 8 + dim bytes for a QuantVec (quant.rs:91-93),
+    // 1 + 4*dim for a FullVec (full.rs:45-47).  The two never coincide for an integer dim.
+    const uint64_t dim = prm.dim;
+    const bool full = psz == 1 + 4 * dim && psz != 9 + dim;
+    if (!full && psz != 9 + dim) return fail(HNSWB200_EIO, "params.dim does not match the point size");
+    std::vector<uint8_t> codes, levels(n);
+    std::vector<float> mins, deltas, vals;
+    if (full) {
+        vals.resize(n * dim);
+        for (uint64_t i = 0; i < n; ++i) {
+            const uint8_t* p = &pb[16 + i * psz];
+            levels[i] = p[0];
+            for (uint64_t j = 0; j < dim; ++j) vals[i * dim + j] = get_f32(p + 1 + 4 * j);
+        }
+    } else {
+        codes.resize(n * dim);
+        mins.resize(n);
+        deltas.resize(n);
+        for (uint64_t i = 0; i < n; ++i) {
+            const uint8_t* p = &pb[16 + i * psz];
+            levels[i] = p[0];
+            mins[i] = get_f32(p + 1);
+            deltas[i] = get_f32(p + 5);
+            memcpy(&codes[i * dim], p + 9, dim);
+        }
+    }
     // layers/<idx>, sorted numerically (template.rs:103-109)
     std::vector<uint64_t> idxs;
     DIR* dd = opendir((d + "/layers").c_str());
@@ -1337,7 +1420,8 @@ int hnswb200_index_load_dir(hnswb200_ctx* c, const char* dir, hnswb200_index** o
     for (uint32_t l = 0; l < nl; ++l) { pid[l] = ids[l].data(); pnb[l] = nb[l].data(); poff[l] = off[l].data(); }
     hnswb200_points* P = nullptr;
     hnswb200_graph* G = nullptr;
-    int rc = hnswb200_points_upload(c, codes.data(), mins.data(), deltas.data(), levels.data(), n, (uint32_t)dim, &P);
+    int rc = full ? hnswb200_points_upload_f32(c, vals.data(), levels.data(), n, (uint32_t)dim, &P)
+                  : hnswb200_points_upload(c, codes.data(), mins.data(), deltas.data(), levels.data(), n, (uint32_t)dim, &P);
     if (rc) return rc;
     rc = hnswb200_graph_upload(c, n, nl, caps.data(), nn.data(), pid.data(), poff.data(), pnb.data(), &G);
     if (rc) { hnswb200_points_destroy(P); return rc; }

@@ -410,7 +410,9 @@ static bool make_map(CUtensorMap* tm, const void* base, uint64_t rows, uint32_t 
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-bool bf_tc_supported(const RecLayout& L) { return L.stride == (uint32_t)TC_K && get_encode() != nullptr; }
+bool bf_tc_supported(const RecLayout& L) {
+    return L.kind == HB_REC_QUANT && L.stride == (uint32_t)TC_K && get_encode() != nullptr;
+}
 
 static ByteMask code_mask(const RecLayout& L) {
     ByteMask m;

@@ -31,7 +31,8 @@ namespace hb {
 
 #define HB_DISPATCH_DIM_B(L, ...)                                                  \
     do {                                                                           \
-        if ((L).dim == 100) { using Q = RegQuery<12, 4>; __VA_ARGS__; }            \
+        if ((L).kind == HB_REC_F32) { using Q = FullQuery; __VA_ARGS__; }          \
+        else if ((L).dim == 100) { using Q = RegQuery<12, 4>; __VA_ARGS__; }       \
         else if ((L).dim == 128) { using Q = RegQuery<16, 0>; __VA_ARGS__; }       \
         else if ((L).dim == 96) { using Q = RegQuery<12, 0>; __VA_ARGS__; }        \
         else if ((L).dim == 50) { using Q = RegQuery<6, 2>; __VA_ARGS__; }         \

@@ -272,10 +272,75 @@ struct SmemQuery {
     }
 };
 
+// ---------------------------------------------------------------------------
+// f32 records (the reference's FullVec, vectors/src/full.rs:23-29):
+//   d = sqrt( sum_i (x_i - y_i)^2 ), ONE strictly sequential f32 sum in element order, no FMA.
+// (x - y)^2 == (y - x)^2 bit for bit, so the orientation does not matter.  The 4 lanes of a group
+// take one 16-float chunk at a time (lane l: floats 4l..4l+3, one 16-byte load) and pass the
+// running sum from lane to lane: every lane adds its four squares to the sum it was handed, and the
+// group keeps the result of the lane whose turn it is.  Zero padding adds +0 to a non-negative sum.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float full_chain16(float s, const uint4& x, const float4& y, u64 nz, int gbase) {
+    const u64 t01 = sub2(pk(__uint_as_float(x.x), __uint_as_float(x.y)), pk(y.x, y.y));
+    const u64 t23 = sub2(pk(__uint_as_float(x.z), __uint_as_float(x.w)), pk(y.z, y.w));
+    float q0, q1, q2, q3;
+    up(fma2(t01, t01, nz), q0, q1);  // rn(t*t): adding -0 never changes a product (header comment)
+    up(fma2(t23, t23, nz), q2, q3);
+#pragma unroll
+    for (int st = 0; st < 4; ++st) {
+        const float t = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(s, q0), q1), q2), q3);
+        s = __shfl_sync(HB_FULL, t, gbase + st);
+    }
+    return s;
+}
+
+struct FullQuery {
+    static constexpr bool kKeepsSmem = true;  // dist() reads the query from shared memory
+    const float* qd;  // natural order, zero-padded to 16*W floats, 16-byte aligned
+    uint32_t W;
+    u64 nz;
+    __device__ __forceinline__ void init(const RecLayout& l, const float* q, int) {
+        qd = q;
+        W = l.W;
+        nz = hb_negzero2;
+    }
+    struct Rec { const uint8_t* p; };  // runtime dimension: nothing is preloaded
+    __device__ __forceinline__ static Rec load(const uint8_t* __restrict__ rec, int) { return Rec{rec}; }
+    __device__ __forceinline__ float dist(const Rec& r, int gl, int gbase) const { return dist(r.p, gl, gbase); }
+    __device__ __forceinline__ float dist(const uint8_t* __restrict__ rec, int gl, int gbase) const {
+        const uint4* p = reinterpret_cast<const uint4*>(rec) + gl;
+        const float4* q = reinterpret_cast<const float4*>(qd) + gl;
+        float s = 0.0f;
+        uint4 w = __ldg(p);
+        for (uint32_t j = 0; j < W; ++j) {
+            const uint4 cur = w;
+            if (j + 1 < W) w = __ldg(p + 4 * (j + 1));  // next chunk in flight during this chunk's chain
+            s = full_chain16(s, cur, q[4 * j], nz, gbase);
+        }
+        return __fsqrt_rn(s);
+    }
+};
+
+__device__ __forceinline__ float full_rec_rec_dist(const RecLayout& L, const uint8_t* __restrict__ ra,
+                                                   const uint8_t* __restrict__ rb, int gl, int gbase) {
+    const uint4* pa = reinterpret_cast<const uint4*>(ra) + gl;
+    const uint4* pb = reinterpret_cast<const uint4*>(rb) + gl;
+    const u64 nz = hb_negzero2;
+    float s = 0.0f;
+    for (uint32_t j = 0; j < L.W; ++j) {
+        const uint4 x = __ldg(pa + 4 * j);
+        const uint4 yb = __ldg(pb + 4 * j);
+        const float4 y = make_float4(__uint_as_float(yb.x), __uint_as_float(yb.y), __uint_as_float(yb.z), __uint_as_float(yb.w));
+        s = full_chain16(s, x, y, nz, gbase);
+    }
+    return __fsqrt_rn(s);
+}
+
 // record <-> record distance, both streamed from memory (Points::distance(a,b),
 // points/src/points.rs:86-93: x = a, y = b).  Runtime dimension.
 __device__ __forceinline__ float rec_rec_dist(const RecLayout& L, const uint8_t* __restrict__ ra,
                                               const uint8_t* __restrict__ rb, int gl, int gbase) {
+    if (L.kind == HB_REC_F32) return full_rec_rec_dist(L, ra, rb, gl, gbase);
     const uint4* pa = reinterpret_cast<const uint4*>(ra);
     const uint4* pb = reinterpret_cast<const uint4*>(rb);
     const float mna = __ldg(reinterpret_cast<const float*>(ra + hb_min_offset(L)));
@@ -362,9 +427,32 @@ __device__ __forceinline__ bool warp_quantise(const float* __restrict__ v, uint3
     return !nan;
 }
 
+// Point::new(vector) for a query (points/src/point.rs:24-30): the values the distance arithmetic sees, written to
+// qd in natural order (src may be qd itself).  QuantVec: quantise, then dequantise (the codes are not kept);
+// FullVec: the vector itself, zero-padded to whole 16-float chunks.  Returns false for a vector the reference would
+// panic on: a NaN (QuantVec), any non-finite value (FullVec: inf - inf would make a NaN distance).
+__device__ __forceinline__ bool warp_prepare_query(const RecLayout& L, const float* src, float* qd, int lane) {
+    if (L.kind == HB_REC_F32) {
+        bool bad = false;
+        for (uint32_t i = lane; i < 16 * L.W; i += 32) {
+            const float x = i < L.dim ? src[i] : 0.0f;
+            bad |= !(fabsf(x) <= 3.4028234664e38f);
+            qd[i] = x;
+        }
+        return !__any_sync(HB_FULL, bad);
+    }
+    float mn, dl;
+    return warp_quantise(src, L.dim, lane, qd, nullptr, mn, dl);
+}
+
 // dequantise a stored record into natural element order (qd[dim])
 __device__ __forceinline__ void warp_dequant_record(const RecLayout& L, const uint8_t* __restrict__ rec,
                                                     int lane, float* qd) {
+    if (L.kind == HB_REC_F32) {  // FullVec: the stored values themselves, padding included
+        const float* r = reinterpret_cast<const float*>(rec);
+        for (uint32_t i = lane; i < 16 * L.W; i += 32) qd[i] = __ldg(r + i);
+        return;
+    }
     const float mn = __ldg(reinterpret_cast<const float*>(rec + hb_min_offset(L)));
     const float dl = __ldg(reinterpret_cast<const float*>(rec + hb_delta_offset(L)));
     for (uint32_t i = lane; i < L.dim; i += 32) {

@@ -42,6 +42,7 @@ struct hnswb200_ctx {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     int num_sms = 148;
+    int vec_type = 0;  // HNSWB200_VEC_*: the vector type of the points created through this context (the reference's VecType)
     uint32_t* d_scratch = nullptr;  // [0] work counter (build), [1] nan flag, [2] overflow flag, ...
     // Work counters of the search launches: a ring of zeroed slots, one per launch, re-zeroed by ONE memset each
     // time the ring wraps.  No memset sits between two consecutive searches, so a search may be launched as the

@@ -21,7 +21,8 @@ namespace hb {
 
 #define HB_DISPATCH_DIM(L, ...)                                                    \
     do {                                                                           \
-        if ((L).dim == 100) { using Q = RegQuery<12, 4>; __VA_ARGS__; }            \
+        if ((L).kind == HB_REC_F32) { using Q = FullQuery; __VA_ARGS__; }          \
+        else if ((L).dim == 100) { using Q = RegQuery<12, 4>; __VA_ARGS__; }       \
         else if ((L).dim == 128) { using Q = RegQuery<16, 0>; __VA_ARGS__; }       \
         else if ((L).dim == 96) { using Q = RegQuery<12, 0>; __VA_ARGS__; }        \
         else if ((L).dim == 50) { using Q = RegQuery<6, 2>; __VA_ARGS__; }         \
@@ -99,6 +100,43 @@ __global__ void __launch_bounds__(256) unpack_kernel(const uint8_t* __restrict__
     }
 }
 
+// FullVec::new (vectors/src/full.rs:18-22): the row itself, here zero-padded to whole 16-float chunks
+__global__ void __launch_bounds__(256) pack_f32_kernel(const float* __restrict__ rows, uint64_t n, RecLayout L,
+                                                       uint8_t* rec, uint32_t* bad_flag) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint64_t nwarps = (uint64_t)gridDim.x * (blockDim.x >> 5);
+    for (uint64_t r = warp; r < n; r += nwarps) {
+        float* rp = reinterpret_cast<float*>(rec + r * L.stride);
+        bool bad = false;
+        for (uint32_t i = lane; i < 16 * L.W; i += 32) {
+            const float x = i < L.dim ? rows[r * L.dim + i] : 0.0f;
+            bad |= !(fabsf(x) <= 3.4028234664e38f);
+            rp[i] = x;
+        }
+        if (bad && bad_flag) atomicOr(bad_flag, 1u);
+    }
+}
+
+// VecBase::get_vals (vectors/src/lib.rs:24-26): the values of a stored vector, natural order
+__global__ void __launch_bounds__(256) record_values_kernel(const uint8_t* __restrict__ rec, uint64_t n, RecLayout L,
+                                                            float* rows) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint64_t nwarps = (uint64_t)gridDim.x * (blockDim.x >> 5);
+    for (uint64_t r = warp; r < n; r += nwarps) {
+        const uint8_t* rp = rec + r * L.stride;
+        if (L.kind == HB_REC_F32) {
+            for (uint32_t i = lane; i < L.dim; i += 32) rows[r * L.dim + i] = reinterpret_cast<const float*>(rp)[i];
+        } else {
+            const float mn = *reinterpret_cast<const float*>(rp + hb_min_offset(L));
+            const float dl = *reinterpret_cast<const float*>(rp + hb_delta_offset(L));
+            for (uint32_t i = lane; i < L.dim; i += 32)
+                rows[r * L.dim + i] = __fadd_rn(__fmul_rn((float)rp[hb_code_offset(L, i)], dl), mn);
+        }
+    }
+}
+
 static inline int grid_for_warps(uint64_t nwarps_needed, int warps_per_block, int cap_blocks = 148 * 16) {
     uint64_t b = (nwarps_needed + warps_per_block - 1) / warps_per_block;
     if (b < 1) b = 1;
@@ -117,6 +155,17 @@ cudaError_t launch_pack(const uint8_t* codes, const float* mins, const float* de
                         const RecLayout& L, uint8_t* rec, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
     pack_kernel<<<grid_for_warps(n, 8), 256, 0, st>>>(codes, mins, deltas, n, L, rec);
+    return cudaGetLastError();
+}
+cudaError_t launch_pack_f32(const float* rows, uint64_t n, const RecLayout& L, uint8_t* rec, uint32_t* bad_flag,
+                            cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    pack_f32_kernel<<<grid_for_warps(n, 8), 256, 0, st>>>(rows, n, L, rec, bad_flag);
+    return cudaGetLastError();
+}
+cudaError_t launch_record_values(const uint8_t* rec, uint64_t n, const RecLayout& L, float* rows, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    record_values_kernel<<<grid_for_warps(n, 8), 256, 0, st>>>(rec, n, L, rows);
     return cudaGetLastError();
 }
 cudaError_t launch_unpack(const uint8_t* rec, uint64_t n, const RecLayout& L, uint8_t* codes,
@@ -162,8 +211,7 @@ __global__ void __launch_bounds__(128) dist_query_many_kernel(const uint8_t* __r
     const int gl = lane & 3, gbase = lane & ~3, grp = lane >> 2;
     const uint32_t qd_cap = (L.dim + 7) / 8 * 8 + 8;
     float* qd = reinterpret_cast<float*>(smem) + (size_t)wib * qd_cap;
-    float mn, dl;
-    bool ok = warp_quantise(query, L.dim, lane, qd, nullptr, mn, dl);
+    bool ok = warp_prepare_query(L, query, qd, lane);
     if (!ok && lane == 0 && nan_flag) atomicOr(nan_flag, 1u);
     __syncwarp();
     Q q;
@@ -365,15 +413,14 @@ __global__ void __launch_bounds__(SEARCH_WPB * 32, 5) search_kernel(SearchParams
         qi = __shfl_sync(HB_FULL, qi, 0);
         if (qi >= p.nq) break;
         __syncwarp();
-        // Point::new(vector): the query is quantised exactly like a stored point (template.rs:313)
-        float mn, dl;
+        // Point::new(vector): the query becomes a point exactly like a stored one (template.rs:313)
         // one read of the f32 query (it may live in pinned host memory: see hnswb200_search), then quantise in place
         {
             const float* src = (qi < p.split ? p.queries : p.queries_tail) + (size_t)qi * p.L.dim;
             for (uint32_t i = lane; i < p.L.dim; i += 32) qd[i] = src[i];
         }
         __syncwarp();
-        bool ok = warp_quantise(qd, p.L.dim, lane, qd, nullptr, mn, dl);
+        bool ok = warp_prepare_query(p.L, qd, qd, lane);
         __syncwarp();
         uint32_t* oid = p.out_ids + (size_t)qi * p.topn;
         float* od = p.out_dists ? p.out_dists + (size_t)qi * p.topn : nullptr;
@@ -459,15 +506,14 @@ __global__ void __launch_bounds__(SEARCH_WPB * 32, reg_min_blocks(KPL)) search_k
         qi = __shfl_sync(HB_FULL, qi, 0);
         if (qi >= p.nq) break;
         __syncwarp();
-        // Point::new(vector): the query is quantised exactly like a stored point (template.rs:313)
-        float mn, dl;
+        // Point::new(vector): the query becomes a point exactly like a stored one (template.rs:313)
         // one read of the f32 query (it may live in pinned host memory: see hnswb200_search), then quantise in place
         {
             const float* src = (qi < p.split ? p.queries : p.queries_tail) + (size_t)qi * p.L.dim;
             for (uint32_t i = lane; i < p.L.dim; i += 32) qd[i] = src[i];
         }
         __syncwarp();
-        bool ok = warp_quantise(qd, p.L.dim, lane, qd, nullptr, mn, dl);
+        bool ok = warp_prepare_query(p.L, qd, qd, lane);
         __syncwarp();
         uint32_t* oid = p.out_ids + (size_t)qi * p.topn;
         float* od = p.out_dists ? p.out_dists + (size_t)qi * p.topn : nullptr;

@@ -51,6 +51,11 @@ cudaError_t launch_quantise(const float* rows, uint64_t n, const RecLayout& L, u
                             cudaStream_t st);
 cudaError_t launch_pack(const uint8_t* codes, const float* mins, const float* deltas, uint64_t n,
                         const RecLayout& L, uint8_t* rec, cudaStream_t st);
+// f32 records (FullVec): rows -> zero-padded records (flag raised on a non-finite value); records -> the values the
+// distance arithmetic sees, natural order (works for both kinds: dequantised values of a QuantVec record)
+cudaError_t launch_pack_f32(const float* rows, uint64_t n, const RecLayout& L, uint8_t* rec, uint32_t* bad_flag,
+                            cudaStream_t st);
+cudaError_t launch_record_values(const uint8_t* rec, uint64_t n, const RecLayout& L, float* rows, cudaStream_t st);
 cudaError_t launch_unpack(const uint8_t* rec, uint64_t n, const RecLayout& L, uint8_t* codes,
                           float* mins, float* deltas, cudaStream_t st);
 // rows / |row| (cosine mode); out may alias rows

@@ -18,6 +18,14 @@
 //   one extra 16-byte word at offset 64*W: [min f32][delta f32][rem bytes][pad]
 // stride = 64*W + 16*tail bytes: 128 B for dim 96/100 (one line per candidate),
 // 144 B for dim 128, 64 B for dim 50.
+//
+// f32 records (kind == HB_REC_F32; the reference's other VecType, FullVec, vectors/src/full.rs:3-6):
+// the dim floats in natural order, zero-padded to a multiple of 16 floats.  FullVec::distance sums
+// strictly sequentially (full.rs:23-29), so the 4 lanes of a group take the 16-float chunks of the
+// record in order, lane l holding floats 4l..4l+3 of a chunk (one 16-byte load each, 64 contiguous
+// bytes per group), and hand the running sum from lane to lane.  A padding element contributes
+// (0 - 0)^2 = +0 to a non-negative sum, which leaves it unchanged bit for bit.
+// stride = 64 * ceil(dim/16) bytes: 448 B for dim 100, 512 B for dim 128.
 #pragma once
 #include <stdint.h>
 
@@ -27,7 +35,10 @@
 #define HB_HD inline
 #endif
 
+enum : uint32_t { HB_REC_QUANT = 0, HB_REC_F32 = 1 };
+
 struct RecLayout {
+    uint32_t kind;    // HB_REC_QUANT (QuantVec) or HB_REC_F32 (FullVec)
     uint32_t dim;     // 8*nch + rem
     uint32_t nch;     // full 8-element chunks
     uint32_t rem;     // remainder elements (all accumulate into acc[0])
@@ -45,6 +56,7 @@ HB_HD constexpr uint32_t hb_layout_tail(uint32_t nch, uint32_t rem) {
 
 HB_HD RecLayout hb_make_layout(uint32_t dim) {
     RecLayout L;
+    L.kind = HB_REC_QUANT;
     L.dim = dim;
     L.nch = dim / 8;
     L.rem = dim % 8;
@@ -54,7 +66,23 @@ HB_HD RecLayout hb_make_layout(uint32_t dim) {
     return L;
 }
 
-// byte offset of element i of the vector inside its record
+// f32 records: W = number of 16-float chunks (one 16-byte word per lane per chunk); nch/rem/tail unused
+HB_HD RecLayout hb_make_layout_f32(uint32_t dim) {
+    RecLayout L;
+    L.kind = HB_REC_F32;
+    L.dim = dim;
+    L.nch = dim / 8;
+    L.rem = dim % 8;
+    L.W = (dim + 15) / 16 == 0 ? 1u : (dim + 15) / 16;
+    L.tail = 0;
+    L.stride = 64 * L.W;
+    return L;
+}
+HB_HD RecLayout hb_make_layout_kind(uint32_t dim, uint32_t kind) {
+    return kind == HB_REC_F32 ? hb_make_layout_f32(dim) : hb_make_layout(dim);
+}
+
+// byte offset of element i of the vector inside its record (quantised records)
 HB_HD uint32_t hb_code_offset(const RecLayout& L, uint32_t i) {
     if (i < 8 * L.nch) {
         uint32_t k = i / 8, r = i % 8, l = r / 2, p = 2 * k + (r & 1);

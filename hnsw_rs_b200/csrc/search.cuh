@@ -146,6 +146,14 @@ struct Vis16 {
 __device__ __forceinline__ void prefetch_l2(const void* p) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
+// every 128-byte line of one record (f32 records span several)
+__device__ __forceinline__ void prefetch_record(const uint8_t* rp8, uint32_t rec_stride) {
+    prefetch_l2(rp8);
+    if (rec_stride > 128) {
+        prefetch_l2(rp8 + 128);
+        for (uint32_t o = 256; o < rec_stride; o += 128) prefetch_l2(rp8 + o);
+    }
+}
 
 // ---------------------------------------------------------------------------
 // sorted key list in shared memory, lane-major access
@@ -335,8 +343,7 @@ __device__ __forceinline__ void search_layer(const Q& query, const uint8_t* __re
                 // a second memory latency)
                 if (isnew) {
                     const uint8_t* rp8 = rec + (size_t)nb * rec_stride;
-                    prefetch_l2(rp8);
-                    if (rec_stride > 128) prefetch_l2(rp8 + 128);
+                    prefetch_record(rp8, rec_stride);
                 }
                 unsigned nm = __ballot_sync(HB_FULL, isnew);
                 int ncnt = __popc(nm);

@@ -164,8 +164,7 @@ __device__ __forceinline__ void search_query_reg(const Q& query, const uint8_t* 
         // (about half of the neighbours turn out to be visited already: DRAM has the headroom, the issue slots do not)
         if (valid) {
             const uint8_t* rp8 = rec + (size_t)nb * rec_stride;
-            prefetch_l2(rp8);
-            if (rec_stride > 128) prefetch_l2(rp8 + 128);
+            prefetch_record(rp8, rec_stride);
         }
 #endif
         bool ovf = false;
@@ -194,8 +193,7 @@ __device__ __forceinline__ void search_query_reg(const Q& query, const uint8_t* 
                 // do not pay a second memory latency
                 if (!HB_PREFETCH_ALL && my >= 8) {
                     const uint8_t* rp8 = rec + (size_t)nb * rec_stride;
-                    prefetch_l2(rp8);
-                    if (rec_stride > 128) prefetch_l2(rp8 + 128);
+                    prefetch_record(rp8, rec_stride);
                 }
             }
             __syncwarp();

@@ -21,16 +21,25 @@ from .points import SimplePoints
 
 class HNSW:
     METRICS = {"l2": 0, "cosine": 1}  # HNSWB200_METRIC_*
+    VEC_TYPES = {"quant": 0, "full": 1}  # HNSWB200_VEC_*: the reference's `type VecType` (points/src/point.rs:4)
 
-    def __init__(self, m=12, ef_cons=None, dim=0, ctx=None, _handle=None, metric="l2"):
+    def __init__(self, m=12, ef_cons=None, dim=0, ctx=None, _handle=None, metric="l2", vec_type="quant"):
         self.ctx = ctx or Context.default()
         self._params0 = Params.from_m(m, dim) if ef_cons is None else Params.from_m_efcons(m, ef_cons, dim)
         self.h = _handle  # hnswb200_index*, created by the first insert_bulk / load
         self._metric = self.METRICS[metric]
+        self._vec_type = self.VEC_TYPES[vec_type]
 
     @staticmethod
-    def new(m, ef_cons, dim, ctx=None, metric="l2"):  # template.rs:133-144; metric="cosine" is an addition (unit-norm rows and queries)
-        return HNSW(m, ef_cons, dim, ctx, metric=metric)
+    def new(m, ef_cons, dim, ctx=None, metric="l2", vec_type="quant"):
+        """template.rs:133-144.  metric="cosine" is an addition (unit-norm rows and queries); vec_type="full" is the index
+        the reference builds when its VecType alias is flipped to FullVec (f32 vectors, strictly sequential distance)."""
+        return HNSW(m, ef_cons, dim, ctx, metric=metric, vec_type=vec_type)
+
+    @property
+    def vec_type(self):
+        code = int(lib().hnswb200_points_vec_type(lib().hnswb200_index_points(self.h))) if self.h else self._vec_type
+        return "full" if code == 1 else "quant"
 
     @property
     def metric(self):
@@ -83,16 +92,17 @@ class HNSW:
                 raise HnswB200Error(_ffi.C.c_int(-1).value,
                                     f"The current index dimension is {prm.dim}, but tried inserting points of dimension {d}")
             h = _ffi.vp()
-            if self._metric:
-                # HNSW::new (empty index), choose the metric, then insert_bulk
+            # HNSW::new (empty index) with this index's VecType, choose the metric, then insert_bulk
+            prev = int(lib().hnswb200_ctx_vec_type(self.ctx.h))
+            check(lib().hnswb200_ctx_set_vec_type(self.ctx.h, self._vec_type))
+            try:
                 check(lib().hnswb200_build(self.ctx.h, None, 0, d, C.byref(prm), None, b, C.byref(h)))
-                self.h = h
-                check(lib().hnswb200_index_set_metric(self.h, self._metric))
-                check(lib().hnswb200_index_insert_bulk(self.ctx.h, self.h, ptr(rows, _ffi.f32p), n, d, ptr(lv, _ffi.u8p), b))
-                return self
-            check(lib().hnswb200_build(self.ctx.h, ptr(rows, _ffi.f32p), n, d, C.byref(prm), ptr(lv, _ffi.u8p), b,
-                                       C.byref(h)))
+            finally:
+                lib().hnswb200_ctx_set_vec_type(self.ctx.h, prev)
             self.h = h
+            if self._metric:
+                check(lib().hnswb200_index_set_metric(self.h, self._metric))
+            check(lib().hnswb200_index_insert_bulk(self.ctx.h, self.h, ptr(rows, _ffi.f32p), n, d, ptr(lv, _ffi.u8p), b))
         else:
             check(lib().hnswb200_index_insert_bulk(self.ctx.h, self.h, ptr(rows, _ffi.f32p), n, d,
                                                    ptr(lv, _ffi.u8p), b))
@@ -225,7 +235,8 @@ class HNSW:
     # ---- flat-array import (an index built elsewhere, e.g. by the reference) ----
     @staticmethod
     def from_parts(params, codes, mins, deltas, levels, layers, caps=None, ctx=None):
-        """layers: list of (node_ids, offsets, nbrs) CSR triples, layer 0 first."""
+        """layers: list of (node_ids, offsets, nbrs) CSR triples, layer 0 first.  mins is None and deltas is None:
+        `codes` holds the f32 values of a FullVec index."""
         ctx = ctx or Context.default()
         pts = SimplePoints.from_parts(codes, mins, deltas, levels, ctx)
         L = len(layers)

@@ -10,9 +10,10 @@ import numpy as np
 
 from . import _ffi
 from ._ffi import Context, check, f32, lib, ptr, u32
-from .vectors import QuantVec
+from .vectors import FullVec, QuantVec
 
-VecType = QuantVec  # points/src/point.rs:4
+VecType = QuantVec  # points/src/point.rs:4 (the reference's default; SimplePoints(vec_type="full") stores FullVec)
+VEC_TYPES = {"quant": 0, "full": 1}  # HNSWB200_VEC_*
 
 
 class Point:
@@ -80,9 +81,9 @@ class SimplePoints:
             self.h = None
 
     @staticmethod
-    def new(vecs, ml=None, levels=None, ctx=None):
+    def new(vecs, ml=None, levels=None, ctx=None, vec_type="quant"):
         """points.rs:39-48.  Levels: `levels` if given, else all 0 (the level draw belongs to
-        HNSW::store_points in this design; see hnswb200_build)."""
+        HNSW::store_points in this design; see hnswb200_build).  vec_type="full": `type VecType = FullVec`."""
         ctx = ctx or Context.default()
         rows = f32(vecs)
         if rows.ndim != 2:
@@ -90,12 +91,30 @@ class SimplePoints:
         n, d = rows.shape
         lv = None if levels is None else np.ascontiguousarray(levels, np.uint8)
         h = _ffi.vp()
-        check(lib().hnswb200_points_from_f32(ctx.h, ptr(rows, _ffi.f32p), n, d, ptr(lv, _ffi.u8p), C.byref(h)))
+        if VEC_TYPES[vec_type]:
+            check(lib().hnswb200_points_upload_f32(ctx.h, ptr(rows, _ffi.f32p), ptr(lv, _ffi.u8p), n, d, C.byref(h)))
+        else:
+            check(lib().hnswb200_points_from_f32(ctx.h, ptr(rows, _ffi.f32p), n, d, ptr(lv, _ffi.u8p), C.byref(h)))
         return SimplePoints(ctx, h)
+
+    @property
+    def vec_type(self):
+        return "full" if int(lib().hnswb200_points_vec_type(self.h)) == 1 else "quant"
+
+    def values(self):
+        """get_vals of every point (vectors/src/lib.rs:24-26): (rows[n, dim], levels[n])"""
+        n, d = self.len(), int(lib().hnswb200_points_dim(self.h))
+        rows = np.zeros((n, d), np.float32)
+        levels = np.zeros(n, np.uint8)
+        check(lib().hnswb200_points_values(self.ctx.h, self.h, ptr(rows, _ffi.f32p), ptr(levels, _ffi.u8p)))
+        return rows, levels
 
     @staticmethod
     def from_parts(codes, mins, deltas, levels=None, ctx=None):
+        """mins is None and deltas is None: `codes` holds the f32 values of FullVec points."""
         ctx = ctx or Context.default()
+        if mins is None and deltas is None:
+            return SimplePoints.new(codes, levels=levels, ctx=ctx, vec_type="full")
         codes = np.ascontiguousarray(codes, np.uint8)
         n, d = codes.shape
         mins, deltas = f32(mins), f32(deltas)
@@ -129,10 +148,18 @@ class SimplePoints:
     def get_point(self, idx):  # points.rs:75-77 (None when out of range)
         if idx < 0 or idx >= self.len():
             return None
+        if self.vec_type == "full":
+            rows, levels = self.values()
+            return Point(idx, levels[idx], FullVec(rows[idx]))
         codes, mins, deltas, levels = self.download()
         return Point(idx, levels[idx], QuantVec(deltas[idx], mins[idx], codes[idx]))
 
     def get_points_iter(self, indices):
+        if self.vec_type == "full":
+            rows, levels = self.values()
+            for i in indices:
+                yield Point(i, levels[i], FullVec(rows[i]))
+            return
         codes, mins, deltas, levels = self.download()
         for i in indices:
             yield Point(i, levels[i], QuantVec(deltas[i], mins[i], codes[i]))
@@ -166,9 +193,17 @@ class SimplePoints:
 
     # Serializer, points.rs:119-146
     def size(self):
-        return 16 + self.len() * (9 + (self.dim() or 0))
+        d = self.dim() or 0
+        return 16 + self.len() * ((1 + 4 * d) if self.vec_type == "full" else (9 + d))
 
     def serialize(self):
+        if self.vec_type == "full":  # point.rs:55-61 + full.rs:55-61
+            rows, levels = self.values()
+            n, d = rows.shape
+            rec = np.zeros((n, 1 + 4 * d), np.uint8)
+            rec[:, 0] = levels
+            rec[:, 1:] = rows.astype(">f4").view(np.uint8).reshape(n, 4 * d)
+            return struct.pack(">QQ", n, 1 + 4 * d) + rec.tobytes()
         codes, mins, deltas, levels = self.download()
         n, d = codes.shape
         rec = np.zeros((n, 9 + d), np.uint8)
@@ -179,10 +214,14 @@ class SimplePoints:
         return struct.pack(">QQ", n, 9 + d) + rec.tobytes()
 
     @staticmethod
-    def deserialize(data, ctx=None):
+    def deserialize(data, ctx=None, vec_type="quant"):
+        """The byte string does not name its VecType (the reference fixes it at compile time): say which."""
         n, psz = struct.unpack(">QQ", bytes(data[:16]))
         rec = np.frombuffer(bytes(data[16:16 + n * psz]), np.uint8).reshape(n, psz)
         levels = rec[:, 0].copy()
+        if VEC_TYPES[vec_type]:
+            rows = rec[:, 1:].copy().view(">f4").astype(np.float32).reshape(n, (psz - 1) // 4)
+            return SimplePoints.new(rows, levels=levels, ctx=ctx, vec_type="full")
         mins = rec[:, 1:5].copy().view(">f4").astype(np.float32).reshape(n)
         deltas = rec[:, 5:9].copy().view(">f4").astype(np.float32).reshape(n)
         return SimplePoints.from_parts(rec[:, 9:].copy(), mins, deltas, levels, ctx)

@@ -40,6 +40,9 @@ extern "C" {
  * L2 distances.  The metric is not part of the reference's save format: set it again after hnswb200_index_load_dir. */
 #define HNSWB200_METRIC_L2 0
 #define HNSWB200_METRIC_COSINE 1
+/* the reference's `type VecType` (points/src/point.rs:4): what a Point stores and which distance it evaluates */
+#define HNSWB200_VEC_QUANT 0 /* QuantVec: u8 codes + min + delta, distance_unrolled (vectors/src/quant.rs:14-37); the default */
+#define HNSWB200_VEC_FULL 1  /* FullVec: the f32 values, strictly sequential sum (vectors/src/full.rs:23-29) */
 
 typedef struct hnswb200_ctx hnswb200_ctx;
 typedef struct hnswb200_points hnswb200_points;
@@ -72,6 +75,13 @@ void hnswb200_ctx_destroy(hnswb200_ctx* ctx);
 int hnswb200_ctx_set_stream(hnswb200_ctx* ctx, void* cuda_stream);
 int hnswb200_ctx_sync(hnswb200_ctx* ctx);
 int hnswb200_ctx_device(const hnswb200_ctx* ctx);
+/* HNSWB200_VEC_*: the reference chooses its vector type at compile time (`type VecType = QuantVec;`,
+ * points/src/point.rs:4); here it is a property of the context.  Point sets created through the context afterwards
+ * (points_from_f32, build, an index loaded from a directory keeps the type its file holds) store that type;
+ * existing point sets keep theirs, and every distance, search, build and brute-force entry point follows the type of
+ * the points it is given.  FullVec points must be finite (a NaN distance makes the reference panic). */
+int hnswb200_ctx_set_vec_type(hnswb200_ctx* ctx, int vec_type);
+int hnswb200_ctx_vec_type(const hnswb200_ctx* ctx);
 
 /* Params::from_m / from_m_efcons (params.rs:19-44); ef_cons < 0 -> 2*m */
 void hnswb200_params_default(uint64_t m, int64_t ef_cons, uint64_t dim, hnswb200_params* out);
@@ -96,6 +106,13 @@ int hnswb200_points_from_f32(hnswb200_ctx* ctx, const float* rows, uint64_t n, u
                              const uint8_t* levels, hnswb200_points** out);
 int hnswb200_points_download(hnswb200_ctx* ctx, const hnswb200_points* p, uint8_t* codes, float* mins,
                              float* deltas, uint8_t* levels);
+/* FullVec points (VecType = FullVec, vectors/src/full.rs:18-22) whatever the context's type (levels may be NULL) */
+int hnswb200_points_upload_f32(hnswb200_ctx* ctx, const float* rows, const uint8_t* levels, uint64_t n, uint32_t dim,
+                               hnswb200_points** out);
+/* VecBase::get_vals of every point (vectors/src/lib.rs:24-26): rows[n*dim] = the stored f32 values of FullVec
+ * points, the dequantised values of QuantVec points; rows and levels may be NULL */
+int hnswb200_points_values(hnswb200_ctx* ctx, const hnswb200_points* p, float* rows, uint8_t* levels);
+int hnswb200_points_vec_type(const hnswb200_points* p);
 /* HNSWB200_METRIC_*; may only change while the object holds no points */
 int hnswb200_points_set_metric(hnswb200_points* p, int metric);
 int hnswb200_points_metric(const hnswb200_points* p);

@@ -242,12 +242,18 @@ class HNSW {
 
     // template.rs:133-144.  metric: HNSWB200_METRIC_L2 (the reference) or HNSWB200_METRIC_COSINE (an addition: rows and
     // queries are L2-normalised on the device, then the reference's L2 path runs on the unit vectors)
+    // vec_type: HNSWB200_VEC_QUANT (the reference as committed, `type VecType = QuantVec;`, points/src/point.rs:4) or
+    // HNSWB200_VEC_FULL (the same alias flipped to FullVec: f32 vectors, FullVec::distance)
     static HNSW new_(size_t m, std::optional<size_t> ef_cons, size_t dim, Context& c = Context::global(),
-                     int metric = HNSWB200_METRIC_L2) {
+                     int metric = HNSWB200_METRIC_L2, int vec_type = HNSWB200_VEC_QUANT) {
         hnswb200_params p;
         hnswb200_params_default(m, ef_cons ? (int64_t)*ef_cons : -1, dim, &p);
         hnswb200_index* ix = nullptr;
-        check(hnswb200_build(c.get(), nullptr, 0, (uint32_t)dim, &p, nullptr, 0, &ix));
+        const int prev = hnswb200_ctx_vec_type(c.get());
+        check(hnswb200_ctx_set_vec_type(c.get(), vec_type));
+        const int brc = hnswb200_build(c.get(), nullptr, 0, (uint32_t)dim, &p, nullptr, 0, &ix);
+        hnswb200_ctx_set_vec_type(c.get(), prev);
+        check(brc);
         if (metric != HNSWB200_METRIC_L2) {
             int rc = hnswb200_index_set_metric(ix, metric);
             if (rc) { hnswb200_index_destroy(ix); check(rc); }
@@ -255,6 +261,7 @@ class HNSW {
         return HNSW(&c, ix);
     }
     int metric() const { return hnswb200_index_metric(ix_); }
+    int vec_type() const { return hnswb200_points_vec_type(hnswb200_index_points(ix_)); }
     HNSW(HNSW&& o) noexcept : params(o.params), ctx_(o.ctx_), ix_(o.ix_) { o.ix_ = nullptr; }
     HNSW& operator=(HNSW&& o) noexcept {
         if (this != &o) {

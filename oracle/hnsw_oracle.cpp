@@ -58,6 +58,9 @@ struct QuantVec {
     float delta = 0.f;
     float min = 0.f;
     std::vector<uint8_t> codes;
+    // vectors/src/full.rs:3-6: when the index was created with VecType = FullVec (points/src/point.rs:4 flipped) a
+    // point carries its f32 values instead of the three fields above
+    std::vector<float> full;
 };
 
 // Rust `f32 as u8`: saturating, NaN -> 0.
@@ -310,32 +313,63 @@ size_t new_layer(float ml, ChaChaRng& rng) {
 // ---------------------------------------------------------------------------
 struct Points {
     size_t dim = 0;
+    bool full = false;           // VecType = FullVec: `vals` is the store, FullVec::distance the metric
     std::vector<uint8_t> codes;  // n * dim
     std::vector<float> mins, deltas;
+    std::vector<float> vals;     // n * dim (full mode)
     std::vector<uint8_t> levels;
-    size_t len() const { return mins.size(); }
+    size_t len() const { return levels.size(); }
+    // Point::new (points/src/point.rs:24-30): VecType::new(vector)
+    bool make_point(const float* v, size_t d, QuantVec& out) const;
     void push(const QuantVec& q, uint8_t level) {
-        codes.insert(codes.end(), q.codes.begin(), q.codes.end());
-        mins.push_back(q.min);
-        deltas.push_back(q.delta);
+        if (full) {
+            vals.insert(vals.end(), q.full.begin(), q.full.end());
+        } else {
+            codes.insert(codes.end(), q.codes.begin(), q.codes.end());
+            mins.push_back(q.min);
+            deltas.push_back(q.delta);
+        }
         levels.push_back(level);
+    }
+    // the stored point `id` as a value (get_point(id).clone())
+    void get(uint32_t id, QuantVec& out) const {
+        if (full) {
+            out.full.assign(&vals[(size_t)id * dim], &vals[(size_t)(id + 1) * dim]);
+        } else {
+            out.delta = deltas[id];
+            out.min = mins[id];
+            out.codes.assign(&codes[(size_t)id * dim], &codes[(size_t)(id + 1) * dim]);
+        }
     }
     // points.rs:86-93  distance(a,b) = a.dist2other(b)
     float distance(uint32_t a, uint32_t b) const {
+        if (full) return dist_sequential(&vals[(size_t)a * dim], &vals[(size_t)b * dim], dim);
         return dist_unrolled(&codes[(size_t)a * dim], deltas[a], mins[a],
                              &codes[(size_t)b * dim], deltas[b], mins[b], dim);
     }
     // points.rs:95-101  distance2point(point, idx) = point.dist2other(points[idx])
     float distance2point(const QuantVec& p, uint32_t b) const {
+        if (full) return dist_sequential(p.full.data(), &vals[(size_t)b * dim], dim);
         return dist_unrolled(p.codes.data(), p.delta, p.min, &codes[(size_t)b * dim], deltas[b],
                              mins[b], dim);
     }
     // point.rs:35-37 via searcher.rs:66-69: index.get_point(node).dist2other(point)
     float node2point(uint32_t a, const QuantVec& p) const {
+        if (full) return dist_sequential(&vals[(size_t)a * dim], p.full.data(), dim);
         return dist_unrolled(&codes[(size_t)a * dim], deltas[a], mins[a], p.codes.data(), p.delta,
                              p.min, dim);
     }
 };
+
+bool Points::make_point(const float* v, size_t d, QuantVec& out) const {
+    if (!full) return quantise(v, d, out);
+    // FullVec::new clones the vector (full.rs:18-22).  A non-finite value can make a NaN distance, on which the
+    // reference panics (graph/src/dist.rs:32): refused here, like a NaN in quantise().
+    for (size_t i = 0; i < d; ++i)
+        if (!std::isfinite(v[i])) { g_err = "non-finite value in vector"; return false; }
+    out.full.assign(v, v + d);
+    return true;
+}
 
 // ---------------------------------------------------------------------------
 // hnsw crate
@@ -487,10 +521,7 @@ bool build_insertion_results(Results& r, Index& ix, uint32_t id) {
     r.clear_all();                        // setup_insert, inserter.rs:53-68
     r.ensure(ix.points.len());
     QuantVec point;
-    point.delta = ix.points.deltas[id];
-    point.min = ix.points.mins[id];
-    point.codes.assign(&ix.points.codes[(size_t)id * ix.points.dim],
-                       &ix.points.codes[(size_t)(id + 1) * ix.points.dim]);
+    ix.points.get(id, point);
     size_t level = ix.points.levels[id];
     r.selected.insert(Dist{ix.params.ep, ix.points.distance(ix.params.ep, id)});
     r.evals++;
@@ -568,7 +599,7 @@ bool store_points(Index& ix, const float* rows, size_t n, size_t dim,
     QuantVec q;
     for (size_t i = 0; i < n; ++i) {
         size_t level = forced_levels ? forced_levels[i] : new_layer(ml, rng);
-        if (!quantise(rows + i * dim, dim, q)) return false;
+        if (!ix.points.make_point(rows + i * dim, dim, q)) return false;
         uint32_t id = (uint32_t)ix.points.len();
         ix.points.push(q, (uint8_t)level);
         ids.push_back(id);
@@ -608,7 +639,7 @@ bool insert_bulk(Index& ix, const float* rows, size_t n, size_t dim, const uint8
 bool ann_by_vector(const Index& ix, const float* v, size_t n, size_t ef, Results& r,
                    std::vector<Dist>& out) {
     QuantVec point;
-    if (!quantise(v, ix.params.dim, point)) return false;
+    if (!ix.points.make_point(v, ix.params.dim, point)) return false;
     r.selected.clear();
     r.candidates.clear();
     r.hops = 0;
@@ -675,9 +706,13 @@ bool save_dir(const Index& ix, const std::string& dir) {
     std::vector<uint8_t> b;
     const Points& P = ix.points;
     put_u64(b, P.len());
-    put_u64(b, 9 + P.dim);
+    put_u64(b, P.full ? 1 + 4 * P.dim : 9 + P.dim);  // 1 + VecType::size(): full.rs:45-47 / quant.rs:91-93
     for (size_t i = 0; i < P.len(); ++i) {
         b.push_back(P.levels[i]);
+        if (P.full) {
+            for (size_t j = 0; j < P.dim; ++j) put_f32(b, P.vals[i * P.dim + j]);  // full.rs:55-61
+            continue;
+        }
         put_f32(b, P.mins[i]);
         put_f32(b, P.deltas[i]);
         b.insert(b.end(), &P.codes[i * P.dim], &P.codes[(i + 1) * P.dim]);
@@ -723,18 +758,28 @@ bool load_dir(Index& ix, const std::string& dir) {
     std::vector<uint8_t> b;
     if (!read_file(dir + "/points", b) || b.size() < 16) { g_err = "Problem reading points file"; return false; }
     size_t len = get_u64(&b[0]), psz = get_u64(&b[8]);
-    if (psz < 9 || b.size() < 16 + len * psz) { g_err = "points file truncated"; return false; }
+    if (psz < 5 || b.size() < 16 + len * psz) { g_err = "points file truncated"; return false; }
+    std::vector<uint8_t> pb;
+    pb.swap(b);
+    if (!read_file(dir + "/params", b) || b.size() < 52) { g_err = "Problem reading params file"; return false; }
+    // the VecType the file was written with is not recorded; the point size tells: 1 + 4*dim (FullVec) or 9 + dim
+    const size_t pdim = get_u64(&b[36]);
     Points& P = ix.points;
     P = Points();
-    P.dim = psz - 9;
+    P.dim = pdim;
+    P.full = psz == 1 + 4 * pdim && psz != 9 + pdim;
+    if (!P.full && psz != 9 + pdim) { g_err = "params.dim does not match the point size"; return false; }
     for (size_t i = 0; i < len; ++i) {
-        const uint8_t* p = &b[16 + i * psz];
+        const uint8_t* p = &pb[16 + i * psz];
         P.levels.push_back(p[0]);
+        if (P.full) {
+            for (size_t j = 0; j < pdim; ++j) P.vals.push_back(get_f32(p + 1 + 4 * j));
+            continue;
+        }
         P.mins.push_back(get_f32(p + 1));
         P.deltas.push_back(get_f32(p + 5));
         P.codes.insert(P.codes.end(), p + 9, p + psz);
     }
-    if (!read_file(dir + "/params", b) || b.size() < 52) { g_err = "Problem reading params file"; return false; }
     ix.params.m = get_u64(&b[0]); ix.params.mmax = get_u64(&b[8]); ix.params.mmax0 = get_u64(&b[16]);
     ix.params.ml = get_f32(&b[24]);
     ix.params.ef_cons = get_u64(&b[28]); ix.params.dim = get_u64(&b[36]);
@@ -856,6 +901,18 @@ void* oracle_index_new(uint64_t m, int64_t ef_cons, uint64_t dim) {  // template
     return ix;
 }
 void oracle_index_free(void* h) { delete (Index*)h; }
+// VecType of an EMPTY index: 0 = QuantVec (the reference as committed), 1 = FullVec (points/src/point.rs:4 flipped)
+int oracle_set_vec_type(void* h, int full) {
+    Index& ix = *(Index*)h;
+    if (ix.points.len() != 0) { g_err = "the vector type can only be chosen while the index is empty"; return -1; }
+    ix.points.full = full != 0;
+    return 0;
+}
+int oracle_vec_type(void* h) { return ((Index*)h)->points.full ? 1 : 0; }
+void oracle_export_values(void* h, float* vals) {  // FullVec store, n*dim
+    const Points& P = ((Index*)h)->points;
+    if (vals && P.full) memcpy(vals, P.vals.data(), 4 * P.vals.size());
+}
 
 int oracle_insert_bulk(void* h, const float* rows, uint64_t n, uint64_t dim, const uint8_t* levels,
                        uint64_t* evals) {
@@ -927,9 +984,15 @@ void* oracle_index_from_parts(uint64_t m, uint64_t ef_cons, uint64_t dim, uint32
                               const uint32_t* const* nbrs) {
     Index* ix = (Index*)oracle_index_new(m, (int64_t)ef_cons, dim);
     ix->params.ep = ep;
-    ix->points.codes.assign(codes, codes + n * dim);
-    ix->points.mins.assign(mins, mins + n);
-    ix->points.deltas.assign(deltas, deltas + n);
+    if (!mins && !deltas) {  // FullVec parts: `codes` points at n*dim f32 values
+        ix->points.full = true;
+        const float* v = reinterpret_cast<const float*>(codes);
+        ix->points.vals.assign(v, v + n * dim);
+    } else {
+        ix->points.codes.assign(codes, codes + n * dim);
+        ix->points.mins.assign(mins, mins + n);
+        ix->points.deltas.assign(deltas, deltas + n);
+    }
     ix->points.levels.assign(levels, levels + n);
     ix->layers.add_level(n_layers ? n_layers - 1 : 0);
     for (uint64_t l = 0; l < n_layers; ++l) {
@@ -1004,7 +1067,7 @@ int oracle_bruteforce(void* h, const float* queries, uint64_t q, uint64_t k, uin
         std::vector<Dist> out;
         QuantVec qv;
         for (uint64_t i = lo; i < hi; ++i) {
-            if (!quantise(queries + i * ix.params.dim, ix.params.dim, qv)) { failed = 1; return; }
+            if (!ix.points.make_point(queries + i * ix.params.dim, ix.params.dim, qv)) { failed = 1; return; }
             brute_force_one(ix, qv, k, out);
             for (uint64_t j = 0; j < k; ++j) {
                 if (out_ids) out_ids[i * k + j] = j < out.size() ? out[j].id : 0xFFFFFFFFu;
@@ -1026,7 +1089,7 @@ int oracle_bruteforce(void* h, const float* queries, uint64_t q, uint64_t k, uin
 int oracle_dist_query_many(void* h, const float* query, const uint32_t* ids, uint64_t n, float* out) {
     const Index& ix = *(Index*)h;
     QuantVec qv;
-    if (!quantise(query, ix.params.dim, qv)) return -1;
+    if (!ix.points.make_point(query, ix.params.dim, qv)) return -1;
     for (uint64_t i = 0; i < n; ++i) out[i] = ix.points.distance2point(qv, ids[i]);
     return 0;
 }

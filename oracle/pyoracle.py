@@ -52,6 +52,9 @@ def lib():
         L.oracle_index_new.restype = C.c_void_p
         L.oracle_index_new.argtypes = [C.c_uint64, C.c_int64, C.c_uint64]
         L.oracle_index_free.argtypes = [C.c_void_p]
+        L.oracle_set_vec_type.argtypes = [C.c_void_p, C.c_int]
+        L.oracle_vec_type.argtypes = [C.c_void_p]
+        L.oracle_export_values.argtypes = [C.c_void_p, f32p]
         L.oracle_insert_bulk.argtypes = [C.c_void_p, f32p, C.c_uint64, C.c_uint64, u8p, u64p]
         L.oracle_insert_vec.restype = C.c_int64
         L.oracle_insert_vec.argtypes = [C.c_void_p, f32p, C.c_uint64]
@@ -217,11 +220,26 @@ class Graph:
 class Index:
     """Mirror of hnsw::template::HNSW (hnsw/src/template.rs) on the CPU oracle."""
 
-    def __init__(self, m=12, ef_cons=None, dim=0, _handle=None):
+    def __init__(self, m=12, ef_cons=None, dim=0, _handle=None, full=False):
+        """full=True: the index the reference builds with `type VecType = FullVec;` (points/src/point.rs:4)."""
         if _handle is not None:
             self.h = C.c_void_p(_handle)
         else:
             self.h = C.c_void_p(lib().oracle_index_new(m, -1 if ef_cons is None else ef_cons, dim))
+            if full and lib().oracle_set_vec_type(self.h, 1):
+                raise OracleError(last_error())
+
+    @property
+    def full(self): return bool(lib().oracle_vec_type(self.h))
+
+    def export_values(self):
+        """FullVec store: (values[n, dim], levels[n])"""
+        n, d = len(self), self.dim
+        vals = np.zeros((n, d), np.float32)
+        lv = np.zeros(n, np.uint8)
+        lib().oracle_export_values(self.h, _p(vals, f32p))
+        lib().oracle_export_points(self.h, None, None, None, _p(lv, u8p))
+        return vals, lv
 
     def __del__(self):
         if getattr(self, "h", None):
@@ -293,9 +311,12 @@ class Index:
 
     @staticmethod
     def from_parts(m, ef_cons, dim, ep, codes, mins, deltas, levels, layers):
-        codes = np.ascontiguousarray(codes, np.uint8)
-        mins = np.ascontiguousarray(mins, np.float32)
-        deltas = np.ascontiguousarray(deltas, np.float32)
+        """mins is None and deltas is None: `codes` holds the f32 values of a FullVec index."""
+        full = mins is None and deltas is None
+        codes = np.ascontiguousarray(codes, np.float32 if full else np.uint8)
+        if not full:
+            mins = np.ascontiguousarray(mins, np.float32)
+            deltas = np.ascontiguousarray(deltas, np.float32)
         levels = np.ascontiguousarray(levels, np.uint8)
         L = len(layers)
         keep = []
@@ -312,8 +333,9 @@ class Index:
             ids_arr[l] = _p(ids, u32p)
             off_arr[l] = _p(off, u64p)
             nb_arr[l] = _p(nb, u32p)
-        h = lib().oracle_index_from_parts(m, ef_cons, dim, ep, mins.shape[0], _p(codes, u8p), _p(mins, f32p),
-                                          _p(deltas, f32p), _p(levels, u8p), L, _p(nn, u64p), ids_arr,
+        h = lib().oracle_index_from_parts(m, ef_cons, dim, ep, levels.shape[0], _p(codes, u8p),
+                                          None if full else _p(mins, f32p),
+                                          None if full else _p(deltas, f32p), _p(levels, u8p), L, _p(nn, u64p), ids_arr,
                                           off_arr, nb_arr)
         return Index(_handle=h)
 

@@ -110,11 +110,14 @@ static void can_not_add_different_dim() {  // #[should_panic]
     ASSERT(panicked);
 }
 static std::string g_data;
+static int g_vec_type = HNSWB200_VEC_QUANT;  // the suite's index tests run once per VecType (points/src/point.rs:4)
 static void hnsw_glove_build_eval() {
     auto stored = hnsw_rs::hnsw::helpers::load_glove_array(0, g_data + "/store.txt");
     auto queries = hnsw_rs::hnsw::helpers::load_glove_array(0, g_data + "/queries.txt");
     ASSERT(stored.size() == 1000 && queries.size() == 100);
-    HNSW index = HNSW::new_(M, std::nullopt, queries[0].size()).insert_bulk(stored, 1, false);
+    HNSW index = HNSW::new_(M, std::nullopt, queries[0].size(), Context::global(), HNSWB200_METRIC_L2, g_vec_type)
+                     .insert_bulk(stored, 1, false);
+    ASSERT(index.vec_type() == g_vec_type);
     // ground truth: all distance2point values sorted by Dist, first 10 ids (template.rs:531-541)
     auto queries_nn = hnsw_rs::hnsw::helpers::brute_force_nns(10, index, queries);
     size_t total_hits = 0;
@@ -138,14 +141,15 @@ static void hnsw_glove_build_eval() {
 }
 static void hnsw_serialize() {
     for (int rep = 0; rep < 5; ++rep) {
-        HNSW index = HNSW::new_(12, std::nullopt, DIM).insert_bulk(make_rand_vectors(N, DIM), 1, false);
+        HNSW index = HNSW::new_(12, std::nullopt, DIM, Context::global(), HNSWB200_METRIC_L2, g_vec_type)
+                         .insert_bulk(make_rand_vectors(N, DIM), 1, false);
         std::string path = "/tmp/hnsw_rs_serialization_test";
         std::string rm = "rm -rf " + path;
         (void)!std::system(rm.c_str());
         index.save(path);
         HNSW loaded = HNSW::load(path);
         (void)!std::system(rm.c_str());
-        ASSERT(loaded.len() == N);
+        ASSERT(loaded.len() == N && loaded.vec_type() == g_vec_type);
         auto a = index.get_layer(0), b = loaded.get_layer(0);
         ASSERT(a.nodes == b.nodes);
         for (NodeID i = 0; i + 1 < (NodeID)N; ++i) ASSERT(*index.distance(i, i + 1) == *loaded.distance(i, i + 1));
@@ -164,6 +168,9 @@ int main(int argc, char** argv) {
         {"hnsw::hnsw_insert_many_after_build", hnsw_insert_many_after_build},
         {"hnsw::can_not_add_different_dim", can_not_add_different_dim},
         {"hnsw::hnsw_glove_build_eval", hnsw_glove_build_eval}, {"hnsw::hnsw_serialize", hnsw_serialize},
+        // the same two with `type VecType = FullVec;`
+        {"hnsw(FullVec)::hnsw_glove_build_eval", [] { g_vec_type = HNSWB200_VEC_FULL; hnsw_glove_build_eval(); g_vec_type = HNSWB200_VEC_QUANT; }},
+        {"hnsw(FullVec)::hnsw_serialize", [] { g_vec_type = HNSWB200_VEC_FULL; hnsw_serialize(); g_vec_type = HNSWB200_VEC_QUANT; }},
     };
     if (argc > 2 && std::string(argv[2]) == "--list") {
         for (auto& t : tests) std::printf("%s\n", t.name);

@@ -17,7 +17,7 @@ def _build():
 def test_cpp_suite_builds_and_lists():
     _build()
     out = subprocess.run([BIN, GOLDEN, "--list"], capture_output=True, text=True, check=True).stdout.split()
-    assert "hnsw::hnsw_glove_build_eval" in out and "vectors::quant::distance" in out and len(out) == 12
+    assert "hnsw::hnsw_glove_build_eval" in out and "vectors::quant::distance" in out and "hnsw(FullVec)::hnsw_serialize" in out and len(out) == 14
 
 
 def test_cpp_suite_fails_loudly_without_gpu():
@@ -35,7 +35,7 @@ def test_cpp_reference_suite_passes():
     r = subprocess.run([BIN, GOLDEN], capture_output=True, text=True, timeout=600)
     print(r.stdout)
     assert r.returncode == 0, r.stdout[-2000:]
-    assert "12 passed; 0 failed" in r.stdout
+    assert "14 passed; 0 failed" in r.stdout
 
 
 def test_host_edge_store_matches_set_semantics():
