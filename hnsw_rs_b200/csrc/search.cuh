@@ -97,6 +97,9 @@ struct Vis32 {
 // on B-bit ids; home = top t bits of h, rem = low B-t bits.  An entry stores
 // (rem << 4 | displacement) with displacement <= 14, so (slot, entry) determines the id:
 // no false positives, no false negatives.  Needs B - t <= 12.
+#ifndef HB_VIS_STS
+#define HB_VIS_STS 1  // 1: claim entries with a 16-bit store + read-back; 0: 32-bit compare-and-swap on the entry pair (A/B)
+#endif
 struct Vis16 {
     uint32_t* words;  // T/2 words holding two entries each
     uint32_t tbits, bbits;
@@ -120,6 +123,29 @@ struct Vis16 {
         const uint32_t rem16 = (h << tbits) >> (28u - (bbits - tbits));
         uint32_t slot = h >> (32u - tbits), mine = rem16;  // mine = rem16 | displacement
         bool pending = want, isnew = false;
+#if HB_VIS_STS
+        // The table belongs to this warp alone, so an entry is claimed with a plain 16-bit store and read back:
+        // two lanes that claim the same free entry in the same step write different values ((slot, entry) names the
+        // id and the ids of a batch are distinct), so exactly the lane whose value stuck has won, and the loser finds
+        // the entry taken by another id and moves on like any lane that met an occupied entry.  A pending lane
+        // therefore advances by one displacement per step, in lockstep with the (warp-uniform) step counter: the
+        // loop needs no per-lane bookkeeping beyond `pending`, and "window exhausted" is "still pending after 15 steps".
+        volatile uint16_t* tab = reinterpret_cast<volatile uint16_t*>(words);
+#pragma unroll 1
+        for (int it = 0; it < 15 && __any_sync(HB_FULL, pending); ++it) {
+            const uint32_t e = tab[slot];
+            const bool claim = pending && e == 0xFFFFu;
+            if (claim) tab[slot] = (uint16_t)mine;
+            __syncwarp();
+            const bool done = tab[slot] == mine;  // already there (e == mine) or claimed just now
+            isnew = isnew || (claim && done);
+            pending = pending && !done;
+            slot = (slot + 1u) & tmask;
+            ++mine;
+        }
+        if (pending) *ovf = true;
+        return isnew || pending;
+#else
 #pragma unroll 1
         while (__any_sync(HB_FULL, pending)) {
             uint32_t* wp = words + (slot >> 1);
@@ -140,6 +166,7 @@ struct Vis16 {
             pending = pending && !hit && !won && !full;
         }
         return isnew;
+#endif
     }
 };
 

@@ -24,6 +24,10 @@
 #define HB_PREFETCH_ALL 1  // 0: only the records of rounds >= 2 are prefetched, after the visited test
 #endif
 
+#ifndef HB_PIPE_ROUNDS
+#define HB_PIPE_ROUNDS 0  // 1: software-pipelined rounds (the records of the next round are loaded before this one is evaluated)
+#endif
+
 namespace hb {
 
 constexpr u64 RSENT = ~0ull;
@@ -58,31 +62,30 @@ struct RegList {
     // shared memory).  len = number of real keys, updated.
     __device__ __forceinline__ void merge(const u64* kbuf, int m, u64* mbuf, int& len, int ef, int lane) {
         const u64 nk = lane < m ? kbuf[lane] : RSENT;
-        // bit j of ltm[s]: new key j is below this lane's list key s; bit j of ownm: new key j is below this
-        // lane's own new key; myr: number of list keys below this lane's own new key
-        uint32_t ltm[KPL];
+        // shift[s]: number of new keys below this lane's list key s; own: number of new keys below this lane's own
+        // new key; myr: number of list keys below this lane's own new key
+        int shift[KPL];
 #pragma unroll
-        for (int s = 0; s < KPL; ++s) ltm[s] = 0u;
-        uint32_t ownm = 0u;
-        int myr = 0;
+        for (int s = 0; s < KPL; ++s) shift[s] = 0;
+        int own = 0, myr = 0;
 #pragma unroll 1
         for (int j = 0; j < m; ++j) {
             const u64 kj = kbuf[j];  // broadcast read
-            const uint32_t bit = 1u << j;
             int r = 0;
 #pragma unroll
             for (int s = 0; s < KPL; ++s) {
-                const bool ge = !(kj < v[s]);  // list key below the new key (keys are distinct); false for sentinels
-                r += __popc(__ballot_sync(HB_FULL, ge));
-                ltm[s] |= ge ? 0u : bit;
+                // lt = kj < v[s]: new key below this list key (keys are distinct; true for sentinels);
+                // shift[s] += lt; r += number of lanes with !lt.  One predicate feeds the add and the vote
+                // (written out: the compiler evaluated the comparison twice and copied the counters around).
+                uint32_t bal;
+                asm volatile("{\n .reg .pred p;\n setp.lt.u64 p, %2, %3;\n @p add.s32 %0, %0, 1;\n"
+                             " vote.sync.ballot.b32 %1, !p, 0xffffffff;\n}"
+                             : "+r"(shift[s]), "=r"(bal) : "l"(kj), "l"(v[s]));
+                r += __popc(bal);
             }
-            ownm |= (kj < nk) ? bit : 0u;
+            asm("{\n .reg .pred p;\n setp.lt.u64 p, %1, %2;\n @p add.s32 %0, %0, 1;\n}" : "+r"(own) : "l"(kj), "l"(nk));
             myr = lane == j ? r : myr;
         }
-        int shift[KPL];
-#pragma unroll
-        for (int s = 0; s < KPL; ++s) shift[s] = __popc(ltm[s]);
-        const int own = __popc(ownm);
 #pragma unroll
         for (int s = 0; s < KPL; ++s) {
             const int p = lane * KPL + s + shift[s];
@@ -101,24 +104,26 @@ struct RegList {
         }
         __syncwarp();
     }
-    // candidates.pop_first(): the first entry whose "expanded" bit is clear; marks it expanded.
-    // Returns false when there is none.
-    __device__ __forceinline__ bool pop(u64& ck, int lane) {
-        int fs = -1;
-        u64 mine = RSENT;
+    // candidates.pop_first(): the first entry whose "expanded" bit is clear; marks it expanded and returns its id.
+    // Returns false when there is none.  Only the low words are looked at: the flag and the id live there, and the
+    // sentinel's low bit is set, so an empty slot reads as expanded.
+    __device__ __forceinline__ bool pop(uint32_t& cid, int lane) {
+        uint32_t lo[KPL], hi[KPL];
 #pragma unroll
-        for (int s = KPL - 1; s >= 0; --s) {
-            const bool un = !((uint32_t)v[s] & 1u);
-            fs = un ? s : fs;
-            mine = sel64(un, v[s], mine);
-        }
-        const unsigned m = __ballot_sync(HB_FULL, fs >= 0);
+        for (int s = 0; s < KPL; ++s) asm("mov.b64 {%0,%1}, %2;" : "=r"(lo[s]), "=r"(hi[s]) : "l"(v[s]));
+        uint32_t pick = 0xFFFFFFFFu;  // low bit set: nothing to expand in this lane
+#pragma unroll
+        for (int s = KPL - 1; s >= 0; --s) pick = (lo[s] & 1u) ? pick : lo[s];
+        const unsigned m = __ballot_sync(HB_FULL, !(pick & 1u));
         if (!m) return false;
-        const int l = __ffs(m) - 1;
-        ck = __shfl_sync(HB_FULL, mine, l);
-        fs = lane == l ? fs : -1;
+        const uint32_t got = __shfl_sync(HB_FULL, pick, __ffs(m) - 1);
+        cid = got >> 1;
+        // ids are unique in the list, so the low word `got` names its entry: set the "expanded" bit there
 #pragma unroll
-        for (int s = 0; s < KPL; ++s) v[s] |= (s == fs) ? 1ull : 0ull;
+        for (int s = 0; s < KPL; ++s) {
+            lo[s] |= (lo[s] == got) ? 1u : 0u;
+            asm("mov.b64 %0, {%1,%2};" : "=l"(v[s]) : "r"(lo[s]), "r"(hi[s]));
+        }
         return true;
     }
     __device__ __forceinline__ void clear_flags() {  // clear_candidates (searcher.rs:100)
@@ -198,13 +203,28 @@ __device__ __forceinline__ void search_query_reg(const Q& query, const uint8_t* 
             }
             __syncwarp();
             int kcnt = 0;
+#if HB_PIPE_ROUNDS
+            // the record loads of round r+1 are issued before round r is evaluated
+            uint32_t cand_n = newbuf[grp < ncnt ? grp : 0];
+            typename Q::Rec rec_n = Q::load(rec + (size_t)cand_n * rec_stride, gl);
+#endif
 #pragma unroll 1
             for (int r0 = 0; r0 < ncnt; r0 += 8) {
                 const int idx = r0 + grp;
                 const bool act = idx < ncnt;
+#if HB_PIPE_ROUNDS
+                const uint32_t cand = cand_n;
+                const typename Q::Rec rec_c = rec_n;
+                if (r0 + 8 < ncnt) {
+                    cand_n = newbuf[idx + 8 < ncnt ? idx + 8 : 0];
+                    rec_n = Q::load(rec + (size_t)cand_n * rec_stride, gl);
+                }
+                const float d = query.dist(rec_c, gl, gbase);
+#else
                 const uint32_t cand = newbuf[act ? idx : 0];
                 // index.get_point(node).dist2other(point)  (searcher.rs:66-69)
                 const float d = query.dist(rec + (size_t)cand * rec_stride, gl, gbase);
+#endif
                 const u64 key = make_rkey(d, cand);
                 // admission (searcher.rs:74-94): key < list[ef-1] covers |selected| < ef and strict <.
                 // `worst` is the batch's starting value: a key admitted against it may still fall off the end
@@ -228,8 +248,8 @@ __device__ __forceinline__ void search_query_reg(const Q& query, const uint8_t* 
         }
         seed = false;
         if (row == EMPTY_ID) {
-            u64 ck;
-            if (!L.pop(ck, lane)) {
+            uint32_t cid;
+            if (!L.pop(cid, lane)) {
                 // this layer is finished: selected survives as the entry set of the next one
                 L.clear_flags();
                 if (layer == 0) break;
@@ -247,7 +267,6 @@ __device__ __forceinline__ void search_query_reg(const Q& query, const uint8_t* 
             }
             if (STATS) cnt.hops++;
             // layer.neighbors_vec(cid)  (graph/src/graph.rs:103-113) as fixed-stride rows
-            const uint32_t cid = rkey_id(ck);
             row = layer ? __ldg(g.upper_off + cid) + (layer - 1) : cid;
         }
         {

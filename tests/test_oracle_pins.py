@@ -268,3 +268,52 @@ def test_search_order_independence_and_counts(oracle, glove, glove_index):
     for i in range(len(queries)):
         k = [(dists[i, j], ids[i, j]) for j in range(counts[i])]
         assert k == sorted(k)
+
+
+# ---- the oracle's FullVec mode (`type VecType = FullVec;`, points/src/point.rs:4): the same reference tests ----
+def test_fullvec_mode_glove_build_eval(oracle, glove):  # template.rs:518-572 with the alias flipped
+    store, queries = glove
+    ix = oracle.Index(12, None, store.shape[1], full=True).insert_bulk(store)
+    assert ix.full and len(ix) == 1000
+    gt, gd = ix.bruteforce(queries, 10)
+    # the ground truth is the f32 metric itself: FullVec::distance, one sequential sum (full.rs:23-29)
+    for i in (0, 17, 99):
+        s = np.float32(0)
+        for a, b in zip(queries[i], store[gt[i, 0]]):
+            t = np.float32(a) - np.float32(b)
+            s = np.float32(s + np.float32(t * t))
+        assert np.sqrt(s) == gd[i, 0]
+    ids, _, counts, hops, evals = ix.search_batch(queries, 10, 100)
+    hits = sum(len(set(gt[i].tolist()) & set(ids[i, :counts[i]].tolist())) for i in range(len(queries)))
+    assert hits / (len(queries) * 10) > 0.99
+    for l in range(ix.nb_layers):
+        if oracle.lib().oracle_layer_nb_nodes(ix.h, l) <= 1:
+            continue
+        mn, mx = ix.layer_degree_range(l)
+        assert mn > 0 and mx <= int(np.ceil(np.float32(ix.layer_cap(l)) * np.float32(1.1)))
+    with pytest.raises(oracle.OracleError):  # a NaN distance makes the reference panic (graph/src/dist.rs:32)
+        bad = queries[:1].copy()
+        bad[0, 3] = np.nan
+        ix.search_batch(bad, 10, 100)
+
+
+def test_fullvec_mode_save_load_round_trip(oracle, tmp_path):  # template.rs:574-611; point size 1 + 4*dim (full.rs:45-61)
+    rng = np.random.default_rng(12)
+    rows = rng.random((100, 10), dtype=np.float32)
+    ix = oracle.Index(12, None, 10, full=True).insert_bulk(rows)
+    ix.save(tmp_path / "ix")
+    blob = (tmp_path / "ix" / "points").read_bytes()
+    assert len(blob) == 16 + 100 * (1 + 4 * 10)
+    assert np.array_equal(np.frombuffer(blob[16 + 1:16 + 41], ">f4").astype(np.float32), rows[0])
+    ld = oracle.Index.load(tmp_path / "ix")
+    assert ld.full and len(ld) == 100 and ld.ep == ix.ep and ld.params() == ix.params()
+    assert np.array_equal(ld.export_values()[0], rows)
+    for l in range(ix.nb_layers):
+        for a, b in zip(ix.export_layer(l), ld.export_layer(l)):
+            assert np.array_equal(a, b)
+    for i in range(99):
+        assert ix.distance(i, i + 1) == ld.distance(i, i + 1)
+    # a QuantVec directory still loads as one
+    q = oracle.Index(12, None, 10).insert_bulk(rows)
+    q.save(tmp_path / "q")
+    assert not oracle.Index.load(tmp_path / "q").full
