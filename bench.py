@@ -151,10 +151,12 @@ def recall_at_k(ids, gt):
     return hits / gt.size
 
 
-def alg_bytes(hops, nbrs, evals, nq, dim, k):
-    """B_q = sum_layers[hops*8 + 4*deg(expanded) + evals*(8+dim)] + 4*dim + 8*k (counted, not modelled)."""
+def alg_bytes(hops, nbrs, evals, nq, dim, k, rec=None):
+    """SURVEY 8(d): B_q = sum_layers[hops*8 + 4*deg(expanded) + evals*rec] + 4*dim + 8*k (counted, not modelled);
+    rec = 8 + dim bytes per evaluated QuantVec record, 4*dim per FullVec record."""
+    rec = (8 + dim) if rec is None else rec
     return float(hops.astype(np.float64).sum() * 8 + nbrs.astype(np.float64).sum() * 4 +
-                 evals.astype(np.float64).sum() * (8 + dim) + nq * (4 * dim + 8 * k))
+                 evals.astype(np.float64).sum() * rec + nq * (4 * dim + 8 * k))
 
 
 def oracle_from_index(ix):
@@ -215,6 +217,9 @@ def main():
     ap.add_argument("--ef-cons", type=int, default=200)
     ap.add_argument("--ncent", type=int, default=2048)
     ap.add_argument("--ef", type=int, default=0, help="skip the sweep and use this ef")
+    ap.add_argument("--vec-type", default="quant", choices=["quant", "full"],
+                    help="the reference's `type VecType` (points/src/point.rs:4): quant = QuantVec (the reference as committed, the "
+                         "headline); full = FullVec (f32 vectors, strictly sequential distance)")
     ap.add_argument("--save-index", default="", help="HNSW::save the built index here (profiling helper)")
     ap.add_argument("--load-index", default="", help="HNSW::load instead of building (profiling helper)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the oracle timing (profiling helper)")
@@ -245,7 +250,8 @@ def main():
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
 
     workload = (f"C2 synthetic GloVe-100 shape: {a.n_base}x{a.dim} unit-norm clustered mixture ({a.ncent} centres, "
-                f"sigma 0.35, seed 1), {a.n_queries} queries/GPU (seed 2+rank), k={K}, quantised-L2 (== cosine rank)")
+                f"sigma 0.35, seed 1), {a.n_queries} queries/GPU (seed 2+rank), k={K}, " +
+                ("quantised-L2 (== cosine rank)" if a.vec_type == "quant" else "f32 L2, VecType = FullVec (== cosine rank)"))
     queries = synth(a.n_queries, a.dim, a.ncent, 2 + rank)
     nq, dim = queries.shape
 
@@ -255,7 +261,7 @@ def main():
     else:
         base = synth(a.n_base, a.dim, a.ncent, 1)
         t0 = time.time()
-        ix = H.HNSW.new(a.m, a.ef_cons, a.dim, ctx=ctx).insert_bulk(base)
+        ix = H.HNSW.new(a.m, a.ef_cons, a.dim, ctx=ctx, vec_type=a.vec_type).insert_bulk(base)
         del base
     build_s = time.time() - t0
     if a.save_index and rank == 0:
@@ -373,7 +379,8 @@ def main():
     evals = d_e.cpu().numpy().astype(np.uint32)
     nbrs = d_nb.cpu().numpy().astype(np.uint32)
     flags = d_f.cpu().numpy()
-    ab = alg_bytes(hops, nbrs, evals, nq, dim, K)
+    full = ix.vec_type == "full"
+    ab = alg_bytes(hops, nbrs, evals, nq, dim, K, 4 * dim if full else None)
 
     # ---------------- end to end through the host-buffer entry point ----------------
     hq = torch.from_numpy(queries).pin_memory()
@@ -449,11 +456,13 @@ def main():
     achieved = ab / (kern_ms / 1e3) / 1e9
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "search_kernel_traffic.json"))).get("dram_bytes_per_launch")
+        if not full:  # the ncu capture under profiles/ is of the QuantVec kernel on this workload
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "search_kernel_traffic.json"))).get("dram_bytes_per_launch")
     except Exception:
         pass
-    kname = ("hb::search_kernel_reg<RegQuery<12,4>,Vis16,%d,false>" % (2 if ef <= 64 else 4 if ef <= 128 else 8)) if ef <= 256 \
-        else "hb::search_kernel<RegQuery<12,4>,Vis16,0>"
+    qname = "FullQuery" if full else "RegQuery<12,4>"
+    kname = ("hb::search_kernel_reg<%s,Vis16,%d,false>" % (qname, 2 if ef <= 64 else 4 if ef <= 128 else 8)) if ef <= 256 \
+        else "hb::search_kernel<%s,Vis16,0>" % qname
     roofline = {"bound": "hbm", "kernel": kname, "achieved": round(achieved, 1),
                 "peak": peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                 "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
