@@ -388,6 +388,10 @@ __device__ __forceinline__ void make_vis(Vis16& v, unsigned char* mem, const Sea
     v.tbits = p.tbits;
     v.bbits = p.bbits;
 }
+__device__ __forceinline__ void make_vis(Vis16N& v, unsigned char* mem, const SearchParams& p) {
+    v.words = reinterpret_cast<uint32_t*>(mem);
+    v.bbits = p.bbits;
+}
 __device__ __forceinline__ void make_vis(Vis32& v, unsigned char* mem, const SearchParams& p) {
     v.tab = reinterpret_cast<uint32_t*>(mem);
     v.tbits = p.tbits;
@@ -483,9 +487,12 @@ __host__ __device__ inline size_t search_reg_warp_smem(uint32_t tbits, uint32_t 
 #define HB_REG_MINB2 6  // resident blocks per SM the KPL=2 kernel is compiled for (register budget)
 #endif
 constexpr int reg_min_blocks(int kpl) { return kpl <= 2 ? HB_REG_MINB2 : kpl <= 4 ? 5 : 4; }
+// the 3584-entry visited table exists to make room for a seventh block per SM (72 registers)
+template <class VIS> constexpr int reg_min_blocks_for(int kpl) { return reg_min_blocks(kpl); }
+template <> constexpr int reg_min_blocks_for<Vis16N>(int kpl) { return kpl <= 2 ? 7 : reg_min_blocks(kpl); }
 
 template <class Q, class VIS, int KPL, bool STATS>
-__global__ void __launch_bounds__(SEARCH_WPB * 32, reg_min_blocks(KPL)) search_kernel_reg(SearchParams p) {
+__global__ void __launch_bounds__(SEARCH_WPB * 32, reg_min_blocks_for<VIS>(KPL)) search_kernel_reg(SearchParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int gl = lane & 3, gbase = lane & ~3;
@@ -581,6 +588,9 @@ static cudaError_t launch_search_reg_s(const SearchParams& p, int num_sms, cudaS
         if (e != cudaSuccess) return e;
         occ_cache = occ < 1 ? 1 : occ;
         occ_smem = smem;
+        if (getenv("HNSWB200_DEBUG_LAUNCH"))
+            fprintf(stderr, "[hnswb200 search] KPL=%d visited bytes/warp=%zu smem/block=%zu blocks/SM=%d\n", KPL,
+                    VIS::bytes(p.tbits), smem, occ_cache);
     }
     uint64_t want = ((uint64_t)p.nq + SEARCH_WPB - 1) / SEARCH_WPB;
     int occ = occ_cache;
@@ -699,7 +709,11 @@ cudaError_t launch_search(const SearchLaunch& a, int num_sms, cudaStream_t st) {
             cudaError_t e0 = cudaMemsetAsync(a.work_counter, 0, sizeof(uint32_t), st);
             if (e0 != cudaSuccess) return e0;
         }
+        // ef <= 64 with the default 4096-entry table: the 3584-entry table and a seventh block per SM instead (Vis16N).
+        // Only for queries that live in registers (a shared-memory query would take the room of the seventh block).
+        const bool use16n = use16 && a.ef <= 64 && p.tbits == 12 && Vis16N::fits(p.bbits) && !getenv("HNSWB200_VIS_POW2");
         HB_DISPATCH_DIM(a.L, {
+            if (use16n && !Q::kKeepsSmem) return launch_search_reg_t<Q, Vis16N, 2>(p, num_sms, st, a.overlap_previous);
             if (use16) {
                 if (a.ef <= 64) return launch_search_reg_t<Q, Vis16, 2>(p, num_sms, st, a.overlap_previous);
                 if (a.ef <= 128) return launch_search_reg_t<Q, Vis16, 4>(p, num_sms, st, a.overlap_previous);

@@ -170,6 +170,50 @@ struct Vis16 {
     }
 };
 
+// Vis16 with a table that is not a power of two: T = 7 * 512 = 3584 entries (7 KB).  With the 128 + 256 + 512 bytes of
+// the other per-warp buffers a warp then needs 8064 bytes, so SEVEN blocks of four warps fit one SM (28 warps instead of
+// the 24 that a 4096-entry table allows; the kernel is latency bound and gains more from the four extra warps than it
+// loses to the higher load factor).  home = floor(hB * T / 2^B) for the B-bit bijection value hB; the entry stores
+// rem = hB - ceil(home * 2^B / T), the offset of hB inside its home's range, so (slot, entry) still names the id exactly.
+// Needs 12 <= B <= 23 (rem < 4096).
+struct Vis16N {
+    static constexpr uint32_t T = 3584;
+    uint32_t* words;
+    uint32_t bbits;
+    static __host__ __device__ size_t bytes(uint32_t) { return (size_t)2 * T; }
+    static __host__ __device__ bool fits(uint32_t bbits) { return bbits >= 12 && bbits <= 23; }
+    __device__ __forceinline__ void clear(int lane) const {
+        uint4* p = reinterpret_cast<uint4*>(words);
+        const uint4 e = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+        for (uint32_t i = lane; i < T / 8; i += 32) p[i] = e;
+        __syncwarp();
+    }
+    // same contract and the same store-and-read-back protocol as Vis16::insert_warp
+    __device__ __forceinline__ bool insert_warp(uint32_t id, bool want, bool* ovf) const {
+        const uint32_t h = (id * 0x9E3779B1u) << (32u - bbits);  // hB, top-aligned
+        const uint32_t home = __umulhi(h, T);                    // floor(hB * T / 2^B)
+        const uint32_t base = ((home << (bbits - 9u)) + 6u) / 7u;  // ceil(home * 2^B / T), T = 7 * 2^9
+        uint32_t slot = home, mine = ((h >> (32u - bbits)) - base) << 4;  // mine = rem << 4 | displacement
+        bool pending = want, isnew = false;
+        volatile uint16_t* tab = reinterpret_cast<volatile uint16_t*>(words);
+#pragma unroll 1
+        for (int it = 0; it < 15 && __any_sync(HB_FULL, pending); ++it) {
+            const uint32_t e = tab[slot];
+            const bool claim = pending && e == 0xFFFFu;
+            if (claim) tab[slot] = (uint16_t)mine;
+            __syncwarp();
+            const bool done = tab[slot] == mine;
+            isnew = isnew || (claim && done);
+            pending = pending && !done;
+            ++slot;
+            slot = slot == T ? 0u : slot;
+            ++mine;
+        }
+        if (pending) *ovf = true;
+        return isnew || pending;
+    }
+};
+
 __device__ __forceinline__ void prefetch_l2(const void* p) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }

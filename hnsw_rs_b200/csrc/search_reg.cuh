@@ -24,6 +24,9 @@
 #define HB_PREFETCH_ALL 1  // 0: only the records of rounds >= 2 are prefetched, after the visited test
 #endif
 
+#ifndef HB_PREFETCH_NEXT_ROW
+#define HB_PREFETCH_NEXT_ROW 0  // 1: L2 prefetch of the adjacency row of the next-best unexpanded entry at every pop (A/B)
+#endif
 #ifndef HB_PIPE_ROUNDS
 #define HB_PIPE_ROUNDS 0  // 1: software-pipelined rounds (the records of the next round are loaded before this one is evaluated)
 #endif
@@ -125,6 +128,13 @@ struct RegList {
             asm("mov.b64 %0, {%1,%2};" : "=l"(v[s]) : "r"(lo[s]), "r"(hi[s]));
         }
         return true;
+    }
+    // low word of this lane's first entry that is not expanded yet (low bit set: none)
+    __device__ __forceinline__ uint32_t first_unexpanded_lo() const {
+        uint32_t pick = 0xFFFFFFFFu;
+#pragma unroll
+        for (int s = KPL - 1; s >= 0; --s) pick = ((uint32_t)v[s] & 1u) ? pick : (uint32_t)v[s];
+        return pick;
     }
     __device__ __forceinline__ void clear_flags() {  // clear_candidates (searcher.rs:100)
 #pragma unroll
@@ -268,6 +278,14 @@ __device__ __forceinline__ void search_query_reg(const Q& query, const uint8_t* 
             if (STATS) cnt.hops++;
             // layer.neighbors_vec(cid)  (graph/src/graph.rs:103-113) as fixed-stride rows
             row = layer ? __ldg(g.upper_off + cid) + (layer - 1) : cid;
+#if HB_PREFETCH_NEXT_ROW
+            // the adjacency row of the best entry that is still unexpanded: the next pop unless a nearer key is admitted first
+            if (layer == 0) {
+                const uint32_t nx = L.first_unexpanded_lo();
+                const unsigned m2 = __ballot_sync(HB_FULL, !(nx & 1u));
+                if (m2 && lane == __ffs(m2) - 1) prefetch_l2(adj + (size_t)(nx >> 1) * S);
+            }
+#endif
         }
         {
             const uint32_t* rp = adj + (size_t)row * S;

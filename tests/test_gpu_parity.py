@@ -200,7 +200,9 @@ def test_search_synthetic(H, oracle, dim, n, m, efc):
     check_search(H, oracle, orc, queries, 3, 50)
 
 
-PATHS = [{}, {"HNSWB200_GENERAL_PATH": "1"}, {"HNSWB200_VIS32": "1"}, {"HNSWB200_GENERAL_PATH": "1", "HNSWB200_VIS32": "1"}]
+# {} = the default path (ef <= 64: 3584-entry visited table, 7 blocks per SM); VIS_POW2 = the 4096-entry table instead
+PATHS = [{}, {"HNSWB200_VIS_POW2": "1"}, {"HNSWB200_GENERAL_PATH": "1"}, {"HNSWB200_VIS32": "1"},
+         {"HNSWB200_GENERAL_PATH": "1", "HNSWB200_VIS32": "1"}]
 
 
 @pytest.mark.parametrize("env", PATHS)
@@ -696,3 +698,22 @@ def test_two_contexts_search_one_index_concurrently(H, oracle, glove, glove_inde
     for t in ts:
         t.join()
     assert not errors, errors
+
+
+def test_search_small_visited_table_under_heavy_load(H, oracle, monkeypatch):
+    """ef <= 64 runs on the 3584-entry visited table (7 blocks per SM).  Wide rows (M = 32) at ef = 64 fill it far beyond
+    its design load, so many probe windows run out: answers must stay identical to the oracle (list-membership fallback),
+    and identical to the 4096-entry table's."""
+    base = synth(20000, 100, 64, 31)
+    queries = synth(300, 100, 64, 32)
+    orc = oracle.Index(32, 64, 100).insert_bulk(base)
+    ix = to_gpu(H, orc)
+    oids, odists, ocounts, ohops, oevals = orc.search_batch(queries, 10, 64, threads=8)
+    ids, dists, counts, st = ix.ann_batch(queries, 10, 64, with_stats=True)
+    assert np.array_equal(ids, oids) and np.array_equal(bits(dists), bits(odists)) and np.array_equal(counts, ocounts)
+    assert np.array_equal(st["hops"], ohops)
+    clean = st["flags"] == 0
+    assert np.array_equal(st["evals"][clean], oevals[clean]) and (st["evals"] >= oevals).all()
+    monkeypatch.setenv("HNSWB200_VIS_POW2", "1")
+    ids2, dists2, counts2 = ix.ann_batch(queries, 10, 64)
+    assert np.array_equal(ids, ids2) and np.array_equal(bits(dists), bits(dists2))
