@@ -207,8 +207,8 @@ def main():
     os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=100)  # 100 steps = 64 ms of kernels: long enough for the clock sampler
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n-base", type=int, default=1183514)
     ap.add_argument("--n-queries", type=int, default=10000)
@@ -461,7 +461,9 @@ def main():
     except Exception:
         pass
     qname = "FullQuery" if full else "RegQuery<12,4>"
-    kname = ("hb::search_kernel_reg<%s,Vis16,%d,false>" % (qname, 2 if ef <= 64 else 4 if ef <= 128 else 8)) if ef <= 256 \
+    # ef <= 64 with a register-resident query: the 3584-entry visited table and 7 blocks per SM (csrc/search.cuh, Vis16N)
+    vname = "Vis16N" if (ef <= 64 and not full and not os.environ.get("HNSWB200_VIS_POW2")) else "Vis16"
+    kname = ("hb::search_kernel_reg<%s,%s,%d,false>" % (qname, vname, 2 if ef <= 64 else 4 if ef <= 128 else 8)) if ef <= 256 \
         else "hb::search_kernel<%s,Vis16,0>" % qname
     roofline = {"bound": "hbm", "kernel": kname, "achieved": round(achieved, 1),
                 "peak": peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
