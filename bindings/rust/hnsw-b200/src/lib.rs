@@ -19,6 +19,13 @@ fn check(rc: i32) -> Result<(), String> {
 /// hnsw/src/params.rs:4-12
 pub type Params = sys::hnswb200_params;
 
+/// `type VecType = QuantVec;` (points/src/point.rs:4) is a compile-time choice in the reference; here it is the cargo
+/// feature `full-vec` (FullVec: f32 vectors, strictly sequential distance) handed to the engine's context.
+#[cfg(not(feature = "full-vec"))]
+const VEC_TYPE: i32 = sys::HNSWB200_VEC_QUANT;
+#[cfg(feature = "full-vec")]
+const VEC_TYPE: i32 = sys::HNSWB200_VEC_FULL;
+
 pub struct HNSW {
     ctx: *mut sys::hnswb200_ctx,
     ix: *mut sys::hnswb200_index,
@@ -34,6 +41,7 @@ impl HNSW {
         unsafe { sys::hnswb200_params_default(m as u64, ef_cons.map(|e| e as i64).unwrap_or(-1), dim as u64, &mut params) };
         let mut ctx = ptr::null_mut();
         check(unsafe { sys::hnswb200_ctx_create(0, &mut ctx) }).expect("no CUDA device: this engine has no CPU fallback");
+        check(unsafe { sys::hnswb200_ctx_set_vec_type(ctx, VEC_TYPE) }).unwrap();
         let mut ix = ptr::null_mut();
         check(unsafe { sys::hnswb200_build(ctx, ptr::null(), 0, dim as u32, &params, ptr::null(), 0, &mut ix) }).unwrap();
         HNSW { ctx, ix, params }
