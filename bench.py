@@ -461,8 +461,8 @@ def main():
     except Exception:
         pass
     qname = "FullQuery" if full else "RegQuery<12,4>"
-    # ef <= 64 with a register-resident query: the 3584-entry visited table and 7 blocks per SM (csrc/search.cuh, Vis16N)
-    vname = "Vis16N" if (ef <= 64 and not full and not os.environ.get("HNSWB200_VIS_POW2")) else "Vis16"
+    # ef <= 64: the 3584-entry visited table (csrc/search.cuh, Vis16N): 7 blocks per SM, 6 for a FullVec index
+    vname = "Vis16N" if (ef <= 64 and not os.environ.get("HNSWB200_VIS_POW2")) else "Vis16"
     kname = ("hb::search_kernel_reg<%s,%s,%d,false>" % (qname, vname, 2 if ef <= 64 else 4 if ef <= 128 else 8)) if ef <= 256 \
         else "hb::search_kernel<%s,Vis16,0>" % qname
     roofline = {"bound": "hbm", "kernel": kname, "achieved": round(achieved, 1),

@@ -113,6 +113,7 @@ __device__ __forceinline__ float group_sum_sqrt(u64 acc, int gl, int gbase) {
 template <int NCH, int REM>
 struct RegQuery {
     static constexpr bool kKeepsSmem = false;  // the dequantised values are copied to registers by init()
+    static constexpr bool kPrefetchBeforeVisited = true;  // records of one or two lines: see search_reg.cuh
     static constexpr int W = (int)hb_layout_W(NCH);
     static constexpr int TAIL = (int)hb_layout_tail(NCH, REM);
     static constexpr int RP = (REM + 1) / 2;  // remainder pairs
@@ -231,6 +232,7 @@ struct RegQuery {
 // ---------------------------------------------------------------------------
 struct SmemQuery {
     static constexpr bool kKeepsSmem = true;  // dist() reads the dequantised values from shared memory
+    static constexpr bool kPrefetchBeforeVisited = true;
     const float* qd;
     RecLayout L;
     __device__ __forceinline__ void init(const RecLayout& l, const float* q, int) {
@@ -296,6 +298,7 @@ __device__ __forceinline__ float full_chain16(float s, const uint4& x, const flo
 
 struct FullQuery {
     static constexpr bool kKeepsSmem = true;  // dist() reads the query from shared memory
+    static constexpr bool kPrefetchBeforeVisited = false;  // 4*dim bytes per record: only records that will be evaluated
     const float* qd;  // natural order, zero-padded to 16*W floats, 16-byte aligned
     uint32_t W;
     u64 nz;
@@ -311,10 +314,13 @@ struct FullQuery {
         const uint4* p = reinterpret_cast<const uint4*>(rec) + gl;
         const float4* q = reinterpret_cast<const float4*>(qd) + gl;
         float s = 0.0f;
-        uint4 w = __ldg(p);
+        // two chunks in flight while one chunk's chain runs (a chain is ~160 cycles, an L2 hit ~300)
+        uint4 w0 = __ldg(p);
+        uint4 w1 = W > 1 ? __ldg(p + 4) : w0;
         for (uint32_t j = 0; j < W; ++j) {
-            const uint4 cur = w;
-            if (j + 1 < W) w = __ldg(p + 4 * (j + 1));  // next chunk in flight during this chunk's chain
+            const uint4 cur = w0;
+            w0 = w1;
+            if (j + 2 < W) w1 = __ldg(p + 4 * (j + 2));
             s = full_chain16(s, cur, q[4 * j], nz, gbase);
         }
         return __fsqrt_rn(s);

@@ -488,11 +488,15 @@ __host__ __device__ inline size_t search_reg_warp_smem(uint32_t tbits, uint32_t 
 #endif
 constexpr int reg_min_blocks(int kpl) { return kpl <= 2 ? HB_REG_MINB2 : kpl <= 4 ? 5 : 4; }
 // the 3584-entry visited table exists to make room for a seventh block per SM (72 registers)
-template <class VIS> constexpr int reg_min_blocks_for(int kpl) { return reg_min_blocks(kpl); }
-template <> constexpr int reg_min_blocks_for<Vis16N>(int kpl) { return kpl <= 2 ? 7 : reg_min_blocks(kpl); }
+// (a query that stays in shared memory takes the room of the seventh block: six then, one more than with 4096 entries)
+template <class VIS, class Q> constexpr int reg_min_blocks_for(int kpl) { return reg_min_blocks(kpl); }
+template <> constexpr int reg_min_blocks_for<Vis16N, RegQuery<12, 4>>(int kpl) { return kpl <= 2 ? 7 : reg_min_blocks(kpl); }
+template <> constexpr int reg_min_blocks_for<Vis16N, RegQuery<12, 0>>(int kpl) { return kpl <= 2 ? 7 : reg_min_blocks(kpl); }
+template <> constexpr int reg_min_blocks_for<Vis16N, RegQuery<16, 0>>(int kpl) { return kpl <= 2 ? 7 : reg_min_blocks(kpl); }
+template <> constexpr int reg_min_blocks_for<Vis16N, RegQuery<6, 2>>(int kpl) { return kpl <= 2 ? 7 : reg_min_blocks(kpl); }
 
 template <class Q, class VIS, int KPL, bool STATS>
-__global__ void __launch_bounds__(SEARCH_WPB * 32, reg_min_blocks_for<VIS>(KPL)) search_kernel_reg(SearchParams p) {
+__global__ void __launch_bounds__(SEARCH_WPB * 32, reg_min_blocks_for<VIS, Q>(KPL)) search_kernel_reg(SearchParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int gl = lane & 3, gbase = lane & ~3;
@@ -710,10 +714,10 @@ cudaError_t launch_search(const SearchLaunch& a, int num_sms, cudaStream_t st) {
             if (e0 != cudaSuccess) return e0;
         }
         // ef <= 64 with the default 4096-entry table: the 3584-entry table and a seventh block per SM instead (Vis16N).
-        // Only for queries that live in registers (a shared-memory query would take the room of the seventh block).
+        // A query that lives in registers gets 7 blocks per SM, one that stays in shared memory 6 (5 with 4096 entries).
         const bool use16n = use16 && a.ef <= 64 && p.tbits == 12 && Vis16N::fits(p.bbits) && !getenv("HNSWB200_VIS_POW2");
         HB_DISPATCH_DIM(a.L, {
-            if (use16n && !Q::kKeepsSmem) return launch_search_reg_t<Q, Vis16N, 2>(p, num_sms, st, a.overlap_previous);
+            if (use16n) return launch_search_reg_t<Q, Vis16N, 2>(p, num_sms, st, a.overlap_previous);
             if (use16) {
                 if (a.ef <= 64) return launch_search_reg_t<Q, Vis16, 2>(p, num_sms, st, a.overlap_previous);
                 if (a.ef <= 128) return launch_search_reg_t<Q, Vis16, 4>(p, num_sms, st, a.overlap_previous);

@@ -176,8 +176,9 @@ __device__ __forceinline__ void search_query_reg(const Q& query, const uint8_t* 
         const bool valid = !(nb & CHAIN_BIT);  // EMPTY_ID and chain markers carry bit 31
 #if HB_PREFETCH_ALL
         // request the record of every neighbour before the visited test: the memory latency overlaps the hash probing
-        // (about half of the neighbours turn out to be visited already: DRAM has the headroom, the issue slots do not)
-        if (valid) {
+        // (about half of the neighbours turn out to be visited already: DRAM has the headroom, the issue slots do not).
+        // Not for f32 records: at four lines per record the wasted half costs more DRAM time than the overlap saves.
+        if (Q::kPrefetchBeforeVisited && valid) {
             const uint8_t* rp8 = rec + (size_t)nb * rec_stride;
             prefetch_record(rp8, rec_stride);
         }
@@ -206,7 +207,7 @@ __device__ __forceinline__ void search_query_reg(const Q& query, const uint8_t* 
                 newbuf[my] = nb;
                 // records of the second and later rounds are requested now, so that those rounds
                 // do not pay a second memory latency
-                if (!HB_PREFETCH_ALL && my >= 8) {
+                if ((!HB_PREFETCH_ALL && my >= 8) || !Q::kPrefetchBeforeVisited) {
                     const uint8_t* rp8 = rec + (size_t)nb * rec_stride;
                     prefetch_record(rp8, rec_stride);
                 }
