@@ -24,12 +24,6 @@
 #define HB_PREFETCH_ALL 1  // 0: only the records of rounds >= 2 are prefetched, after the visited test
 #endif
 
-#ifndef HB_PREFETCH_NEXT_ROW
-#define HB_PREFETCH_NEXT_ROW 0  // 1: L2 prefetch of the adjacency row of the next-best unexpanded entry at every pop (A/B)
-#endif
-#ifndef HB_PIPE_ROUNDS
-#define HB_PIPE_ROUNDS 0  // 1: software-pipelined rounds (the records of the next round are loaded before this one is evaluated)
-#endif
 
 namespace hb {
 
@@ -129,13 +123,6 @@ struct RegList {
         }
         return true;
     }
-    // low word of this lane's first entry that is not expanded yet (low bit set: none)
-    __device__ __forceinline__ uint32_t first_unexpanded_lo() const {
-        uint32_t pick = 0xFFFFFFFFu;
-#pragma unroll
-        for (int s = KPL - 1; s >= 0; --s) pick = ((uint32_t)v[s] & 1u) ? pick : (uint32_t)v[s];
-        return pick;
-    }
     __device__ __forceinline__ void clear_flags() {  // clear_candidates (searcher.rs:100)
 #pragma unroll
         for (int s = 0; s < KPL; ++s) v[s] = sel64(v[s] != RSENT, v[s] & ~1ull, v[s]);
@@ -214,28 +201,13 @@ __device__ __forceinline__ void search_query_reg(const Q& query, const uint8_t* 
             }
             __syncwarp();
             int kcnt = 0;
-#if HB_PIPE_ROUNDS
-            // the record loads of round r+1 are issued before round r is evaluated
-            uint32_t cand_n = newbuf[grp < ncnt ? grp : 0];
-            typename Q::Rec rec_n = Q::load(rec + (size_t)cand_n * rec_stride, gl);
-#endif
 #pragma unroll 1
             for (int r0 = 0; r0 < ncnt; r0 += 8) {
                 const int idx = r0 + grp;
                 const bool act = idx < ncnt;
-#if HB_PIPE_ROUNDS
-                const uint32_t cand = cand_n;
-                const typename Q::Rec rec_c = rec_n;
-                if (r0 + 8 < ncnt) {
-                    cand_n = newbuf[idx + 8 < ncnt ? idx + 8 : 0];
-                    rec_n = Q::load(rec + (size_t)cand_n * rec_stride, gl);
-                }
-                const float d = query.dist(rec_c, gl, gbase);
-#else
                 const uint32_t cand = newbuf[act ? idx : 0];
                 // index.get_point(node).dist2other(point)  (searcher.rs:66-69)
                 const float d = query.dist(rec + (size_t)cand * rec_stride, gl, gbase);
-#endif
                 const u64 key = make_rkey(d, cand);
                 // admission (searcher.rs:74-94): key < list[ef-1] covers |selected| < ef and strict <.
                 // `worst` is the batch's starting value: a key admitted against it may still fall off the end
@@ -279,14 +251,6 @@ __device__ __forceinline__ void search_query_reg(const Q& query, const uint8_t* 
             if (STATS) cnt.hops++;
             // layer.neighbors_vec(cid)  (graph/src/graph.rs:103-113) as fixed-stride rows
             row = layer ? __ldg(g.upper_off + cid) + (layer - 1) : cid;
-#if HB_PREFETCH_NEXT_ROW
-            // the adjacency row of the best entry that is still unexpanded: the next pop unless a nearer key is admitted first
-            if (layer == 0) {
-                const uint32_t nx = L.first_unexpanded_lo();
-                const unsigned m2 = __ballot_sync(HB_FULL, !(nx & 1u));
-                if (m2 && lane == __ffs(m2) - 1) prefetch_l2(adj + (size_t)(nx >> 1) * S);
-            }
-#endif
         }
         {
             const uint32_t* rp = adj + (size_t)row * S;
