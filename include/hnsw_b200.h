@@ -101,7 +101,8 @@ int hnswb200_dist_full_pairs(hnswb200_ctx* ctx, const float* x, const float* y, 
 /* from already quantised parts (levels may be NULL = all 0) */
 int hnswb200_points_upload(hnswb200_ctx* ctx, const uint8_t* codes, const float* mins, const float* deltas,
                            const uint8_t* levels, uint64_t n, uint32_t dim, hnswb200_points** out);
-/* SimplePoints::new without the level draw: quantise f32 rows on the device and keep them there */
+/* SimplePoints::new without the level draw: VecType::new of every row on the device (quantised, or kept as f32 when the
+ * context's vector type is HNSWB200_VEC_FULL), device resident */
 int hnswb200_points_from_f32(hnswb200_ctx* ctx, const float* rows, uint64_t n, uint32_t dim,
                              const uint8_t* levels, hnswb200_points** out);
 int hnswb200_points_download(hnswb200_ctx* ctx, const hnswb200_points* p, uint8_t* codes, float* mins,
@@ -123,7 +124,8 @@ void hnswb200_points_destroy(hnswb200_points* p);
 int hnswb200_dist_pairs(hnswb200_ctx* ctx, const hnswb200_points* p, const uint32_t* a, const uint32_t* b,
                         uint64_t n, float* out);
 /* Points::distance2point / VecBase::dist2many (points.rs:95-101, vectors/src/lib.rs:17-22):
- * the f32 query is quantised (Point::new) and compared with ids[n] */
+ * the f32 query becomes a Point like a stored one (Point::new: quantised for QuantVec points, as it is for FullVec
+ * points) and is compared with ids[n] */
 int hnswb200_dist_query_many(hnswb200_ctx* ctx, const hnswb200_points* p, const float* query,
                              const uint32_t* ids, uint64_t n, float* out);
 
@@ -146,7 +148,7 @@ void hnswb200_graph_destroy(hnswb200_graph* g);
 /* takes ownership of points and graph */
 int hnswb200_index_from_parts(hnswb200_ctx* ctx, hnswb200_points* points, hnswb200_graph* graph,
                               const hnswb200_params* params, hnswb200_index** out);
-/* HNSW::new + insert_bulk (hnsw/src/template.rs:133-144, 388-444): quantise, draw levels, build.
+/* HNSW::new + insert_bulk (hnsw/src/template.rs:133-144, 388-444): VecType::new (the context's vector type), draw levels, build.
  * levels may be NULL (drawn like points.rs:148-160 from the library's own seeded generator).
  * batch = max points inserted concurrently against one frozen graph snapshot (1 = the
  * reference's single-thread order; 0 = library default). */
@@ -204,7 +206,7 @@ int hnswb200_ipc_export(hnswb200_ctx* ctx, void* d_ptr, uint8_t handle[64]);
 int hnswb200_ipc_open(hnswb200_ctx* ctx, const uint8_t handle[64], void** out);
 int hnswb200_ipc_close(hnswb200_ctx* ctx, void* ptr);
 
-/* brute_force_nns (hnsw/src/helpers/glove.rs:73-109): exact top-k under the quantised metric with
+/* brute_force_nns (hnsw/src/helpers/glove.rs:73-109): exact top-k under the metric of the points (quantised, or f32) with
  * (dist, id) order.  id_offset is added to every returned id (global ids of a base shard). */
 int hnswb200_bruteforce_topk(hnswb200_ctx* ctx, const hnswb200_points* base, const float* queries,
                              uint64_t nq, uint32_t k, uint32_t id_offset, uint32_t* out_ids,
