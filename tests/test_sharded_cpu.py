@@ -26,7 +26,7 @@ def np_merge(ids, dists):
     return oi, od
 
 
-def _worker(rank, world, port, mode, out_dir):
+def _worker(rank, world, port, mode, out_dir, full=False):
     sys.path.insert(0, ROOT)
     import torch.distributed as dist
     from oracle import pyoracle as O
@@ -36,7 +36,7 @@ def _worker(rank, world, port, mode, out_dir):
     store = O.load_glove(os.path.join(GOLDEN, "store.txt"))
     queries = O.load_glove(os.path.join(GOLDEN, "queries.txt"))[:37]  # 37: not divisible by 2 -> padding path
     if mode == "query":
-        ix = O.Index(12, None, store.shape[1]).insert_bulk(store)
+        ix = O.Index(12, None, store.shape[1], full=full).insert_bulk(store)
         s = sharded.QueryShardedSearch(None, local_search=lambda q, n, ef: ix.search_batch(q, n, ef)[:3])
         ids, dists, counts = s.search(queries, 10, 40)
         ref = ix.search_batch(queries, 10, 40)
@@ -48,7 +48,7 @@ def _worker(rank, world, port, mode, out_dir):
         ok = ok and np.array_equal(ids, ref[0]) and np.array_equal(counts, ref[2]) and (counts == 4).all()
     else:
         lo, hi = sharded.split_range(len(store), rank, world)
-        shard = O.Index(12, None, store.shape[1]).insert_bulk(store[lo:hi])
+        shard = O.Index(12, None, store.shape[1], full=full).insert_bulk(store[lo:hi])
         s = sharded.BaseShardedSearch(None, lo, local_search=lambda q, n, ef: shard.search_batch(q, n, ef)[:2],
                                       merge=np_merge)
         ids, dists = s.search(queries, 10, 60)
@@ -56,15 +56,15 @@ def _worker(rank, world, port, mode, out_dir):
         parts = []
         for r in range(world):
             a, b = sharded.split_range(len(store), r, world)
-            sh = O.Index(12, None, store.shape[1]).insert_bulk(store[a:b])
+            sh = O.Index(12, None, store.shape[1], full=full).insert_bulk(store[a:b])
             i, d = sh.search_batch(queries, 10, 60)[:2]
             parts.append((np.where(i != 0xFFFFFFFF, i + np.uint32(a), i), d))
         ei, ed = np_merge(np.stack([p[0] for p in parts]), np.stack([p[1] for p in parts]))
         ok = np.array_equal(ids, ei) and np.array_equal(dists.view(np.uint32), ed.view(np.uint32))
         # base-sharded exact brute force == unsharded brute force
-        full = O.Index(12, None, store.shape[1]).insert_bulk(store)
+        whole = O.Index(12, None, store.shape[1], full=full).insert_bulk(store)
         bi, bd = s.bruteforce(queries, 10, local_bruteforce=lambda q, k: shard.bruteforce(q, k))
-        fi, fd = full.bruteforce(queries, 10)
+        fi, fd = whole.bruteforce(queries, 10)
         ok = ok and np.array_equal(bi, fi) and np.array_equal(bd.view(np.uint32), fd.view(np.uint32))
     open(os.path.join(out_dir, f"ok_{mode}_{rank}"), "w").write("1" if ok else "0")
     dist.barrier()
@@ -79,11 +79,12 @@ def _free_port():
     return p
 
 
+@pytest.mark.parametrize("full", [False, True])  # QuantVec (the reference as committed) and FullVec shards
 @pytest.mark.parametrize("mode", ["query", "base"])
-def test_sharded_world2_gloo(oracle, tmp_path, mode):
+def test_sharded_world2_gloo(oracle, tmp_path, mode, full):
     import torch.multiprocessing as mp
     port = _free_port()
-    mp.spawn(_worker, args=(2, port, mode, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, mode, str(tmp_path), full), nprocs=2, join=True)
     for r in range(2):
         assert open(tmp_path / f"ok_{mode}_{r}").read() == "1"
 
