@@ -272,3 +272,20 @@ def test_full_save_load_cross_with_oracle(H, oracle, glove, glove_full, tmp_path
     assert blob == (tmp_path / "cpu" / "points").read_bytes()
     again = H.SimplePoints.deserialize(blob, vec_type="full")
     assert np.array_equal(bits(again.values()[0]), bits(glove_full.export_values()[0]))
+
+
+# ---- committed expected outputs (tests/golden/expected_*.npz, written by the oracle): the device engine end to end ----
+@pytest.mark.parametrize("name,vec_type", [("quant", "quant"), ("full", "full")])
+def test_device_reproduces_committed_expected_outputs(H, glove, name, vec_type):
+    """HNSW::new(12, None, 50).insert_bulk(store) in the single-thread order, ann_by_vector at ef 10 / 100 and brute_force_nns
+    through the C ABI against the committed golden outputs: graph, ids, distance bits, counters."""
+    from golden_check import check_against_golden
+    store, queries = glove
+    ix = H.HNSW.new(12, None, store.shape[1], vec_type=vec_type).insert_bulk(store, batch=1)
+
+    def search(q, n, ef):
+        ids, dists, counts, st = ix.ann_batch(q, n, ef, with_stats=True)
+        return ids, dists, counts, st["hops"], st["evals"]
+
+    check_against_golden(name, {"ep": ix.params.ep, "layers": layers_of(ix), "search": search,
+                                "bruteforce": lambda q, k: H.bruteforce_topk(ix._points(), q, k)}, queries)

@@ -317,3 +317,14 @@ def test_fullvec_mode_save_load_round_trip(oracle, tmp_path):  # template.rs:574
     q = oracle.Index(12, None, 10).insert_bulk(rows)
     q.save(tmp_path / "q")
     assert not oracle.Index.load(tmp_path / "q").full
+
+
+# ---- committed expected outputs (tests/golden/expected_*.npz): the oracle rebuilt from source must reproduce them ----
+@pytest.mark.parametrize("name,full", [("quant", False), ("full", True)])
+def test_oracle_reproduces_committed_expected_outputs(oracle, glove, name, full):
+    from golden_check import check_against_golden
+    store, queries = glove
+    ix = oracle.Index(12, None, store.shape[1], full=full).insert_bulk(store)
+    check_against_golden(name, {"ep": ix.ep, "layers": ix.export_layers(),
+                                "search": lambda q, n, ef: ix.search_batch(q, n, ef),
+                                "bruteforce": lambda q, k: ix.bruteforce(q, k)}, queries)
