@@ -184,3 +184,20 @@ def test_new_layer_distribution(H):  # points.rs:148-160: floor(-ln(u) * ml), u 
     assert H.new_layer(ml, Seq([0.0, 1.0, 0.5])) == int(np.floor(-np.log(np.float32(0.5)) * np.float32(ml)))  # 0 and 1 are redrawn
     assert H.new_layer(ml, Seq([0.9])) == 0
     assert H.new_layer(ml, Seq([1e-6])) == 5
+
+
+def test_public_header_is_plain_c(tmp_path):
+    """The drop-in boundary is a C ABI: include/hnsw_b200.h must compile as C99 (no C++-isms, no torch types), and link
+    against the shared library from a C translation unit."""
+    import subprocess
+    src = tmp_path / "use.c"
+    src.write_text('#include "hnsw_b200.h"\n'
+                   'int main(void) { hnswb200_ctx* c = 0; int rc = hnswb200_ctx_create(0, &c);\n'
+                   '  if (rc == 0) { hnswb200_ctx_set_vec_type(c, HNSWB200_VEC_FULL); hnswb200_ctx_destroy(c); }\n'
+                   '  return hnswb200_version() > 0 ? 0 : 1; }\n')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib_dir = os.path.join(root, "hnsw_rs_b200")
+    exe = tmp_path / "use"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(root, "include"),
+                           str(src), "-o", str(exe), "-L", lib_dir, "-lhnsw_b200", "-Wl,-rpath," + lib_dir])
+    assert subprocess.run([str(exe)]).returncode == 0   # runs with or without a device: ctx_create just fails without one
