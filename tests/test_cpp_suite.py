@@ -44,3 +44,10 @@ def test_host_edge_store_matches_set_semantics():
     _build()
     r = subprocess.run([os.path.join(ROOT, "tests", "cpp", "hostgraph_test")], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "all checks passed" in r.stdout, r.stdout[-2000:]
+
+
+def test_record_layouts():
+    """layout.h: the lane-sliced QuantVec record and the padded f32 (FullVec) record, dims 1..520; host only."""
+    _build()
+    r = subprocess.run([os.path.join(ROOT, "tests", "cpp", "layout_test")], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "all checks passed" in r.stdout, r.stdout[-2000:]
