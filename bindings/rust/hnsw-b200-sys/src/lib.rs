@@ -126,6 +126,17 @@ extern "C" {
                                ef: u32, d_out_ids: *mut u32, d_out_dists: *mut f32, d_out_counts: *mut u32,
                                d_hops: *mut u32, d_evals: *mut u32, d_flags: *mut u32, d_nbrs: *mut u32) -> c_int;
 
+    pub fn hnswb200_ctx_set_overlap(ctx: *mut hnswb200_ctx, allow: c_int) -> c_int;
+    pub fn hnswb200_last_search_variant() -> *const c_char;
+    pub fn hnswb200_search_dev_shard(ctx: *mut hnswb200_ctx, ix: *const hnswb200_index, d_queries: *const f32, nq: u64,
+                                     n: u32, ef: u32, id_offset: u32, d_out_ids: *mut u32, d_out_dists: *mut f32,
+                                     d_out_counts: *mut u32, n_peers: u32, peer_ids: *const *mut u32,
+                                     peer_dists: *const *mut f32, row_offset: u64) -> c_int;
+    pub fn hnswb200_peer_put_dev(ctx: *mut hnswb200_ctx, d_src: *const c_void, bytes: u64, n_peers: u32,
+                                 peer_dst: *const *mut c_void) -> c_int;
+    pub fn hnswb200_peer_signal_dev(ctx: *mut hnswb200_ctx, n_peers: u32, peer_flags: *const *mut u32, slot: u32,
+                                    epoch: u32) -> c_int;
+    pub fn hnswb200_peer_wait_dev(ctx: *mut hnswb200_ctx, d_flags: *const u32, n_slots: u32, epoch: u32) -> c_int;
     pub fn hnswb200_search_dev_gather(ctx: *mut hnswb200_ctx, ix: *const hnswb200_index, d_queries: *const f32, nq: u64,
                                       n: u32, ef: u32, d_out_ids: *mut u32, d_out_dists: *mut f32, d_out_counts: *mut u32,
                                       n_peers: u32, peer_ids: *const *mut u32, row_offset: u64) -> c_int;

@@ -45,6 +45,7 @@ SIGNATURES = {
     "hnswb200_ctx_create": (C.c_int, [C.c_int, C.POINTER(vp)]),
     "hnswb200_ctx_destroy": (None, [vp]),
     "hnswb200_ctx_set_stream": (C.c_int, [vp, vp]),
+    "hnswb200_ctx_set_overlap": (C.c_int, [vp, C.c_int]),
     "hnswb200_ctx_sync": (C.c_int, [vp]),
     "hnswb200_ctx_device": (C.c_int, [vp]),
     "hnswb200_ctx_set_vec_type": (C.c_int, [vp, C.c_int]),
@@ -94,6 +95,12 @@ SIGNATURES = {
     "hnswb200_search_dev": (C.c_int, [vp, vp, vp, C.c_uint64, C.c_uint32, C.c_uint32, vp, vp, vp, vp, vp, vp, vp]),
     "hnswb200_search_dev_gather": (C.c_int, [vp, vp, vp, C.c_uint64, C.c_uint32, C.c_uint32, vp, vp, vp, C.c_uint32,
                                              C.POINTER(vp), C.c_uint64]),
+    "hnswb200_last_search_variant": (C.c_char_p, []),
+    "hnswb200_search_dev_shard": (C.c_int, [vp, vp, vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, vp,
+                                            C.c_uint32, C.POINTER(vp), C.POINTER(vp), C.c_uint64]),
+    "hnswb200_peer_put_dev": (C.c_int, [vp, vp, C.c_uint64, C.c_uint32, C.POINTER(vp)]),
+    "hnswb200_peer_signal_dev": (C.c_int, [vp, C.c_uint32, C.POINTER(vp), C.c_uint32, C.c_uint32]),
+    "hnswb200_peer_wait_dev": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32]),
     "hnswb200_dev_alloc": (C.c_int, [vp, C.c_uint64, C.POINTER(vp)]),
     "hnswb200_dev_free": (C.c_int, [vp, vp]),
     "hnswb200_dev_download": (C.c_int, [vp, vp, vp, C.c_uint64]),
@@ -108,6 +115,12 @@ SIGNATURES = {
 }
 
 _lib = None
+
+
+def last_search_variant():
+    """Name of the kernel variant the calling thread's last search ran (hnswb200_last_search_variant)."""
+    s = lib().hnswb200_last_search_variant()
+    return s.decode() if s else ""
 
 
 def lib():
@@ -155,6 +168,11 @@ class Context:
 
     def set_stream(self, cuda_stream_ptr):
         check(lib().hnswb200_ctx_set_stream(self.h, vp(cuda_stream_ptr)))
+
+    def set_overlap(self, allow=True):
+        """Opt in to overlapping consecutive searches on an adopted stream (hnswb200_ctx_set_overlap): the caller
+        promises that no kernel producing a search's query buffer is enqueued between two searches."""
+        check(lib().hnswb200_ctx_set_overlap(self.h, 1 if allow else 0))
 
     def sync(self):
         check(lib().hnswb200_ctx_sync(self.h))

@@ -60,6 +60,7 @@ int hnswb200_ctx::bf_ws_reserve(size_t bytes) {
 }
 
 int hnswb200_ctx::use() const {
+    last_was_search = false;  // whatever the caller enqueues next is not known to be a search (the search entry points re-arm it)
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
     return 0;
@@ -106,6 +107,7 @@ void hnswb200_ctx_destroy(hnswb200_ctx* c) {
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     if (c->d_scratch) cudaFree(c->d_scratch);
     if (c->d_counters) cudaFree(c->d_counters);
+    if (c->d_spill_ws) cudaFree(c->d_spill_ws);
     if (c->h_status) cudaFreeHost(c->h_status);
     if (c->d_ws) cudaFree(c->d_ws);
     if (c->d_bf_ws) cudaFree(c->d_bf_ws);
@@ -123,8 +125,19 @@ int hnswb200_ctx_set_stream(hnswb200_ctx* c, void* s) {
     c->search_seq = 0;
     c->stream = (cudaStream_t)s;
     c->own_stream = false;
+    c->stream_adopted = true;
+    c->last_was_search = false;
     return 0;
 }
+
+int hnswb200_ctx_set_overlap(hnswb200_ctx* c, int allow) {
+    if (!c) return fail(HNSWB200_EINVAL, "ctx is NULL");
+    c->overlap_opt_in = allow != 0;
+    c->last_was_search = false;
+    return 0;
+}
+
+const char* hnswb200_last_search_variant(void) { return hb::last_search_variant(); }
 
 int hnswb200_ctx_sync(hnswb200_ctx* c) {
     if (!c) return fail(HNSWB200_EINVAL, "ctx is NULL");
@@ -837,25 +850,38 @@ static int search_check(const hnswb200_index* ix, uint64_t nq, uint32_t n, uint3
     return 0;
 }
 
+struct SearchExtras {
+    bool prev_was_search = false;  // captured by the entry point BEFORE ctx->use() (which clears the flag)
+    const float* queries_tail = nullptr;
+    uint32_t split = 0;
+    uint32_t n_peers = 0;
+    uint32_t* const* peer_ids = nullptr;
+    float* const* peer_dists = nullptr;
+    uint64_t peer_row0 = 0;
+    uint32_t id_offset = 0;
+};
 static int search_dev_impl(hnswb200_ctx* c, const hnswb200_index* ix, const float* d_queries, uint64_t nq,
                            uint32_t n, uint32_t ef, uint32_t* d_out_ids, float* d_out_dists,
                            uint32_t* d_out_counts, uint32_t* d_hops, uint32_t* d_evals, uint32_t* d_flags,
-                           uint32_t* d_nbrs, uint32_t* nan_any, const float* queries_tail = nullptr, uint32_t split = 0,
-                           uint32_t n_peers = 0, uint32_t* const* peer_ids = nullptr, uint64_t peer_row0 = 0);
+                           uint32_t* d_nbrs, uint32_t* nan_any, const SearchExtras& x);
 
 int hnswb200_search_dev(hnswb200_ctx* c, const hnswb200_index* ix, const float* d_queries, uint64_t nq,
                         uint32_t n, uint32_t ef, uint32_t* d_out_ids, float* d_out_dists,
                         uint32_t* d_out_counts, uint32_t* d_hops, uint32_t* d_evals, uint32_t* d_flags,
                         uint32_t* d_nbrs) {
+    SearchExtras x;
+    x.prev_was_search = c && c->last_was_search;
     return search_dev_impl(c, ix, d_queries, nq, n, ef, d_out_ids, d_out_dists, d_out_counts, d_hops, d_evals, d_flags,
-                           d_nbrs, nullptr);
+                           d_nbrs, nullptr, x);
 }
 
 static int search_dev_impl(hnswb200_ctx* c, const hnswb200_index* ix, const float* d_queries, uint64_t nq,
                            uint32_t n, uint32_t ef, uint32_t* d_out_ids, float* d_out_dists,
                            uint32_t* d_out_counts, uint32_t* d_hops, uint32_t* d_evals, uint32_t* d_flags,
-                           uint32_t* d_nbrs, uint32_t* nan_any, const float* queries_tail, uint32_t split,
-                           uint32_t n_peers, uint32_t* const* peer_ids, uint64_t peer_row0) {
+                           uint32_t* d_nbrs, uint32_t* nan_any, const SearchExtras& x) {
+    const float* queries_tail = x.queries_tail;
+    uint32_t split = x.split;
+    bool prev_search = x.prev_was_search;
     if (!c || !ix || (nq && (!d_queries || !d_out_ids))) return fail(HNSWB200_EINVAL, "search_dev: NULL argument");
     if (nq == 0) return 0;
     int rc = search_check(ix, nq, n, ef);
@@ -873,6 +899,7 @@ static int search_dev_impl(hnswb200_ctx* c, const hnswb200_index* ix, const floa
         d_queries = nqz;
         queries_tail = nullptr;
         split = 0;
+        prev_search = false;  // the search reads what launch_normalise writes: an ordinary, fully ordered launch
     }
     a.rec = ix->points->d_rec;
     a.L = ix->points->L;
@@ -893,17 +920,32 @@ static int search_dev_impl(hnswb200_ctx* c, const hnswb200_index* ix, const floa
     a.nan_any = nan_any;
     a.queries_tail = queries_tail;
     a.split = split;
-    a.n_peers = n_peers;
-    for (uint32_t g = 0; g < n_peers && g < hb::HB_MAX_PEERS; ++g) a.peer_ids[g] = peer_ids[g];
-    a.peer_row0 = peer_row0;
+    a.n_peers = x.n_peers;
+    for (uint32_t g = 0; g < x.n_peers && g < hb::HB_MAX_PEERS; ++g) {
+        a.peer_ids[g] = x.peer_ids[g];
+        a.peer_dists[g] = x.peer_dists ? x.peer_dists[g] : nullptr;
+    }
+    a.peer_row0 = x.peer_row0;
+    a.id_offset = x.id_offset;
     // counter ring (engine.h): slot 0 follows a memset of the whole ring and is an ordinary launch; the other
     // slots are launched as programmatic dependents of whatever kernel precedes them in the stream
     const uint32_t slot = (uint32_t)(c->search_seq++ % hnswb200_ctx::COUNTER_RING);
     if (slot == 0) HB_CUDA(cudaMemsetAsync(c->d_counters, 0, hnswb200_ctx::COUNTER_RING * sizeof(uint32_t), c->stream));
     a.work_counter = c->d_counters + slot;
     a.counter_is_fresh = true;
-    a.overlap_previous = slot != 0 && !getenv("HNSWB200_NO_PDL");
+    if (!c->d_spill_ws) {  // 8 blocks of 4 warps per SM at most
+        const uint32_t warps = (uint32_t)c->num_sms * 32u;
+        HB_CUDA(cudaMalloc((void**)&c->d_spill_ws, (size_t)warps * hnswb200_ctx::SPILL_CAP * 4));
+        c->spill_warps = warps;
+    }
+    a.spill_ws = c->d_spill_ws;
+    a.spill_cap = hnswb200_ctx::SPILL_CAP;
+    a.spill_warps = c->spill_warps;
+    // programmatic dependent launch only directly behind another search of this context (any other
+    // predecessor may write what this search reads), and on an adopted stream only with the caller's opt-in
+    a.overlap_previous = slot != 0 && prev_search && (!c->stream_adopted || c->overlap_opt_in) && !getenv("HNSWB200_NO_PDL");
     HB_CUDA(launch_search(a, c->num_sms, c->stream));
+    c->last_was_search = true;
     return 0;
 }
 
@@ -914,8 +956,62 @@ int hnswb200_search_dev_gather(hnswb200_ctx* c, const hnswb200_index* ix, const 
     if (n_peers && !peer_ids) return fail(HNSWB200_EINVAL, "search_dev_gather: NULL peer list");
     for (uint32_t g = 0; g < n_peers; ++g)
         if (!peer_ids[g]) return fail(HNSWB200_EINVAL, "search_dev_gather: NULL peer buffer");
+    SearchExtras x;
+    x.prev_was_search = c && c->last_was_search;
+    x.n_peers = n_peers;
+    x.peer_ids = peer_ids;
+    x.peer_row0 = row_offset;
     return search_dev_impl(c, ix, d_queries, nq, n, ef, d_out_ids, d_out_dists, d_out_counts, nullptr, nullptr, nullptr,
-                           nullptr, nullptr, nullptr, 0, n_peers, peer_ids, row_offset);
+                           nullptr, nullptr, x);
+}
+
+int hnswb200_search_dev_shard(hnswb200_ctx* c, const hnswb200_index* ix, const float* d_queries, uint64_t nq, uint32_t n,
+                              uint32_t ef, uint32_t id_offset, uint32_t* d_out_ids, float* d_out_dists,
+                              uint32_t* d_out_counts, uint32_t n_peers, uint32_t* const* peer_ids,
+                              float* const* peer_dists, uint64_t row_offset) {
+    if (n_peers > hb::HB_MAX_PEERS) return fail(HNSWB200_EINVAL, "search_dev_shard: at most 8 peer buffers");
+    if (n_peers && (!peer_ids || !peer_dists)) return fail(HNSWB200_EINVAL, "search_dev_shard: NULL peer list");
+    for (uint32_t g = 0; g < n_peers; ++g)
+        if (!peer_ids[g] || !peer_dists[g]) return fail(HNSWB200_EINVAL, "search_dev_shard: NULL peer buffer");
+    if (ix && (uint64_t)id_offset + ix->points->n > (1ull << 31))
+        return fail(HNSWB200_EINVAL, "search_dev_shard: global ids must stay below 2^31");
+    SearchExtras x;
+    x.prev_was_search = c && c->last_was_search;
+    x.n_peers = n_peers;
+    x.peer_ids = peer_ids;
+    x.peer_dists = peer_dists;
+    x.peer_row0 = row_offset;
+    x.id_offset = id_offset;
+    return search_dev_impl(c, ix, d_queries, nq, n, ef, d_out_ids, d_out_dists, d_out_counts, nullptr, nullptr, nullptr,
+                           nullptr, nullptr, x);
+}
+
+// ---- peer exchange without a collective library (kernels.cu) ----
+int hnswb200_peer_put_dev(hnswb200_ctx* c, const void* d_src, uint64_t bytes, uint32_t n_peers, void* const* peer_dst) {
+    if (!c || (bytes && !d_src) || (n_peers && !peer_dst)) return fail(HNSWB200_EINVAL, "peer_put: NULL argument");
+    if (n_peers > hb::HB_MAX_PEERS) return fail(HNSWB200_EINVAL, "peer_put: at most 8 peer buffers");
+    if (bytes % 16 || ((uintptr_t)d_src & 15)) return fail(HNSWB200_EINVAL, "peer_put: size and pointers must be multiples of 16 bytes");
+    for (uint32_t g = 0; g < n_peers; ++g)
+        if (!peer_dst[g] || ((uintptr_t)peer_dst[g] & 15)) return fail(HNSWB200_EINVAL, "peer_put: bad peer pointer");
+    if (c->use()) return HNSWB200_ECUDA;
+    HB_CUDA(hb::launch_peer_put(d_src, bytes, n_peers, peer_dst, c->num_sms, c->stream));
+    return 0;
+}
+int hnswb200_peer_signal_dev(hnswb200_ctx* c, uint32_t n_peers, uint32_t* const* peer_flags, uint32_t slot, uint32_t epoch) {
+    if (!c || (n_peers && !peer_flags)) return fail(HNSWB200_EINVAL, "peer_signal: NULL argument");
+    if (n_peers > hb::HB_MAX_PEERS) return fail(HNSWB200_EINVAL, "peer_signal: at most 8 peers");
+    for (uint32_t g = 0; g < n_peers; ++g)
+        if (!peer_flags[g]) return fail(HNSWB200_EINVAL, "peer_signal: NULL flag array");
+    if (c->use()) return HNSWB200_ECUDA;
+    HB_CUDA(hb::launch_peer_signal(n_peers, peer_flags, slot, epoch, c->stream));
+    return 0;
+}
+int hnswb200_peer_wait_dev(hnswb200_ctx* c, const uint32_t* d_flags, uint32_t n_slots, uint32_t epoch) {
+    if (!c || (n_slots && !d_flags)) return fail(HNSWB200_EINVAL, "peer_wait: NULL argument");
+    if (n_slots > 32) return fail(HNSWB200_EINVAL, "peer_wait: at most 32 flag words");
+    if (c->use()) return HNSWB200_ECUDA;
+    HB_CUDA(hb::launch_peer_wait(d_flags, n_slots, epoch, c->d_status, c->stream));
+    return 0;
 }
 
 // ---- device buffers that other processes of the box can write (CUDA IPC over NVLink / NVSwitch) ----
@@ -975,6 +1071,7 @@ static void* mapped_alias(const void* host) {
 int hnswb200_search_async(hnswb200_ctx* c, const hnswb200_index* ix, const float* queries, uint64_t nq, uint32_t dim,
                           uint32_t n, uint32_t ef, uint32_t* out_ids, float* out_dists, uint32_t* out_counts) {
     if (!c || !ix || (nq && (!queries || !out_ids))) return fail(HNSWB200_EINVAL, "search_async: NULL argument");
+    const bool prev_search = c->last_was_search;
     if (dim != ix->points->L.dim)
         return fail(HNSWB200_EINVAL, "search: query dimension " + std::to_string(dim) + " != index dimension " +
                                          std::to_string(ix->points->L.dim));
@@ -990,8 +1087,10 @@ int hnswb200_search_async(hnswb200_ctx* c, const hnswb200_index* ix, const float
         return fail(HNSWB200_EINVAL, "search_async: every buffer must be page-locked (cudaHostAlloc / cudaHostRegister): "
                                      "the kernel reads and writes them in place");
     // no staging and no copies: the call only launches; consecutive calls overlap on the device
+    SearchExtras x;
+    x.prev_was_search = prev_search;
     return search_dev_impl(c, ix, (const float*)dq, nq, n, ef, (uint32_t*)di, (float*)dd, (uint32_t*)dc, nullptr, nullptr,
-                           nullptr, nullptr, c->d_status);
+                           nullptr, nullptr, c->d_status, x);
 }
 
 int hnswb200_search(hnswb200_ctx* c, const hnswb200_index* ix, const float* queries, uint64_t nq,
@@ -1042,9 +1141,12 @@ int hnswb200_search(hnswb200_ctx* c, const hnswb200_index* ix, const float* quer
     c->h_status[0] = 0;
     const double t_setup = prof_call ? now_us() : 0;
     if (q.staged) HB_CUDA(cudaMemcpyAsync(q.dev, queries, b_head, cudaMemcpyHostToDevice, c->stream));
+    SearchExtras sx;
+    sx.queries_tail = q_tail;
+    sx.split = (uint32_t)first_wave;
     rc = search_dev_impl(c, ix, (const float*)q.dev, nq, n, ef, (uint32_t*)outs[0].dev, (float*)outs[1].dev,
                          (uint32_t*)outs[2].dev, (uint32_t*)outs[3].dev, (uint32_t*)outs[4].dev, (uint32_t*)outs[5].dev,
-                         (uint32_t*)outs[6].dev, c->d_status, q_tail, (uint32_t)first_wave);
+                         (uint32_t*)outs[6].dev, c->d_status, sx);
     if (rc) return rc;
     for (Buf& b : outs)
         if (b.staged) HB_CUDA(cudaMemcpyAsync(b.host, b.dev, b.bytes, cudaMemcpyDeviceToHost, c->stream));

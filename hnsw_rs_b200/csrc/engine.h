@@ -50,6 +50,14 @@ struct hnswb200_ctx {
     static constexpr uint32_t COUNTER_RING = 32;
     uint32_t* d_counters = nullptr;
     uint64_t search_seq = 0;
+    // Programmatic dependent launch of a search is only safe behind another search of this library (a search reads
+    // nothing a previous search writes).  last_was_search is true while the last operation this context enqueued was
+    // a search kernel; every other entry point clears it (use()).  On an adopted stream (set_stream) the caller may
+    // enqueue producers of the query buffer that the library cannot see, so overlap additionally needs the caller's
+    // opt-in (hnswb200_ctx_set_overlap).
+    mutable bool last_was_search = false;
+    bool stream_adopted = false;
+    bool overlap_opt_in = false;
     void* d_ws = nullptr;           // grow-only workspace for the host-buffer entry points
     size_t ws_bytes = 0;
     void* d_norm_ws = nullptr;      // grow-only scratch for the normalised queries of a cosine index
@@ -58,6 +66,9 @@ struct hnswb200_ctx {
     void* d_bf_ws = nullptr;        // grow-only scratch of the brute-force entry points (cudaMalloc per call costs more than the kernels)
     size_t bf_ws_bytes = 0;
     int bf_ws_reserve(size_t bytes);
+    uint32_t* d_spill_ws = nullptr;  // visited-set spill continuation of the search kernel: SPILL_CAP ids per resident warp
+    static constexpr uint32_t SPILL_CAP = 1024;
+    uint32_t spill_warps = 0;
     std::vector<uint32_t> h_flags;
     uint32_t* h_status = nullptr;   // pinned + mapped host word the search kernel raises on a NaN query
     uint32_t* d_status = nullptr;   // its device alias

@@ -16,6 +16,7 @@
 #include "kernels.h"
 #include "search.cuh"
 #include "search_reg.cuh"
+#include "search_params.cuh"
 
 namespace hb {
 
@@ -343,40 +344,7 @@ cudaError_t launch_dist_full_pairs(const float* x, const float* y, uint64_t n, u
 // ---------------------------------------------------------------------------
 // K3: HNSW search, one warp per query, persistent over the batch
 // ---------------------------------------------------------------------------
-struct SearchParams {
-    const uint8_t* rec;
-    RecLayout L;
-    GraphView g;
-    uint32_t n_layers, ep;
-    const float* queries;
-    const float* queries_tail;  // queries [split, nq) are read from here (same indexing); == queries when not split
-    uint32_t split;
-    uint32_t nq, topn, ef;
-    uint32_t kpl;           // keys per lane of the result list (capacity 32*kpl >= ef)
-    uint32_t tbits, bbits;  // visited table: 2^tbits entries; ids < 2^bbits
-    uint32_t qd_cap;
-    uint32_t* out_ids;
-    float* out_dists;
-    uint32_t* out_counts;
-    uint32_t* out_hops;
-    uint32_t* out_evals;
-    uint32_t* out_flags;
-    uint32_t* out_nbrs;
-    uint32_t* work_counter;
-    uint32_t* nan_any;  // may be null; set to 1 when a query holds a NaN (may live in pinned host memory)
-    // fused all-gather of the id rows: row (peer_row0 + q) of every peer buffer also receives the ids of query q
-    // (peer memory mapped into this device: stores travel over NVLink while the other queries keep computing)
-    uint32_t* peer_ids[HB_MAX_PEERS];
-    uint32_t n_peers;
-    uint64_t peer_row0;
-};
 
-__device__ __forceinline__ void put_id(const SearchParams& p, uint32_t* oid, uint32_t qi, uint32_t j, uint32_t v) {
-    oid[j] = v;
-    for (uint32_t g = 0; g < p.n_peers; ++g) p.peer_ids[g][(p.peer_row0 + qi) * p.topn + j] = v;
-}
-
-constexpr int SEARCH_WPB = 4;
 
 template <class VIS>
 __host__ __device__ inline size_t search_warp_smem(uint32_t kpl, uint32_t tbits, uint32_t qd_cap) {
@@ -429,7 +397,7 @@ __global__ void __launch_bounds__(SEARCH_WPB * 32, 5) search_kernel(SearchParams
         uint32_t* oid = p.out_ids + (size_t)qi * p.topn;
         float* od = p.out_dists ? p.out_dists + (size_t)qi * p.topn : nullptr;
         if (!ok) {  // NaN in query: the reference panics; report through flags and an empty result
-            for (uint32_t j = lane; j < p.topn; j += 32) { put_id(p, oid, qi, j, EMPTY_ID); if (od) od[j] = INFINITY; }
+            for (uint32_t j = lane; j < p.topn; j += 32) put_result(p, oid, od, qi, j, EMPTY_ID, INFINITY);
             if (lane == 0) {
                 if (p.out_counts) p.out_counts[qi] = 0;
                 if (p.out_hops) p.out_hops[qi] = 0;
@@ -458,8 +426,7 @@ __global__ void __launch_bounds__(SEARCH_WPB * 32, 5) search_kernel(SearchParams
             u64 k = (j < p.topn && j < p.ef) ? L.list[j] : SENTINEL;
             bool real = k != SENTINEL;
             if (j < p.topn) {
-                put_id(p, oid, qi, j, real ? (uint32_t)k : EMPTY_ID);
-                if (od) od[j] = real ? __uint_as_float((uint32_t)(k >> 32)) : INFINITY;
+                put_result(p, oid, od, qi, j, real ? (uint32_t)k : EMPTY_ID, real ? __uint_as_float((uint32_t)(k >> 32)) : INFINITY);
             }
             got += __popc(__ballot_sync(HB_FULL, real));
         }
@@ -529,7 +496,7 @@ __global__ void __launch_bounds__(SEARCH_WPB * 32, reg_min_blocks_for<VIS, Q>(KP
         uint32_t* oid = p.out_ids + (size_t)qi * p.topn;
         float* od = p.out_dists ? p.out_dists + (size_t)qi * p.topn : nullptr;
         if (!ok) {  // NaN in query: the reference panics; report through flags and an empty result
-            for (uint32_t j = lane; j < p.topn; j += 32) { put_id(p, oid, qi, j, EMPTY_ID); if (od) od[j] = INFINITY; }
+            for (uint32_t j = lane; j < p.topn; j += 32) put_result(p, oid, od, qi, j, EMPTY_ID, INFINITY);
             if (lane == 0) {
                 if (p.out_counts) p.out_counts[qi] = 0;
                 if (p.out_hops) p.out_hops[qi] = 0;
@@ -554,12 +521,11 @@ __global__ void __launch_bounds__(SEARCH_WPB * 32, reg_min_blocks_for<VIS, Q>(KP
             if (j < p.topn) {
                 const u64 k = L.v[s];
                 const bool real = (j < p.ef) && (k != RSENT);
-                put_id(p, oid, qi, j, real ? rkey_id(k) : EMPTY_ID);
-                if (od) od[j] = real ? __uint_as_float((uint32_t)(k >> 32)) : INFINITY;
+                put_result(p, oid, od, qi, j, real ? rkey_id(k) : EMPTY_ID, real ? __uint_as_float((uint32_t)(k >> 32)) : INFINITY);
                 mine += real ? 1u : 0u;
             }
         }
-        for (uint32_t j = 32 * KPL + lane; j < p.topn; j += 32) { put_id(p, oid, qi, j, EMPTY_ID); if (od) od[j] = INFINITY; }
+        for (uint32_t j = 32 * KPL + lane; j < p.topn; j += 32) put_result(p, oid, od, qi, j, EMPTY_ID, INFINITY);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(HB_FULL, mine, o);
         if (lane == 0) {
@@ -696,12 +662,32 @@ cudaError_t launch_search(const SearchLaunch& a, int num_sms, cudaStream_t st) {
     p.work_counter = a.work_counter;
     p.nan_any = a.nan_any;
     p.n_peers = a.n_peers < HB_MAX_PEERS ? a.n_peers : HB_MAX_PEERS;
-    for (uint32_t g = 0; g < HB_MAX_PEERS; ++g) p.peer_ids[g] = g < p.n_peers ? a.peer_ids[g] : nullptr;
+    for (uint32_t g = 0; g < HB_MAX_PEERS; ++g) {
+        p.peer_ids[g] = g < p.n_peers ? a.peer_ids[g] : nullptr;
+        p.peer_dists[g] = g < p.n_peers ? a.peer_dists[g] : nullptr;
+    }
     p.peer_row0 = a.peer_row0;
+    p.id_offset = a.id_offset;
     bool use16;
     choose_visited(a.ef, a.g.S0, a.n_points, &p.tbits, &p.bbits, &use16);
     const bool generic_list = a.ef > 256 || getenv("HNSWB200_GENERAL_PATH");  // env: test knob
     p.kpl = round_up((a.ef + 31) / 32, 2);
+    if (!generic_list && search_fast_supported(a.L, a.ef, a.n_points)) {
+        // the second-generation kernel (csrc/search_fast.cuh): bucketed visited set, one reduction per batch
+        if (!a.counter_is_fresh) {
+            cudaError_t e0 = cudaMemsetAsync(a.work_counter, 0, sizeof(uint32_t), st);
+            if (e0 != cudaSuccess) return e0;
+        }
+        return launch_search_fast(p, a.n_points, num_sms, st, a.overlap_previous, a.spill_ws, a.spill_cap, a.spill_warps);
+    }
+    {
+        char nm[160];
+        const char* qn = a.L.kind == HB_REC_F32 ? "FullQuery" : (a.L.dim == 100 || a.L.dim == 128 || a.L.dim == 96 || a.L.dim == 50) ? "RegQuery" : "SmemQuery";
+        const bool u16n = use16 && a.ef <= 64 && p.tbits == 12 && Vis16N::fits(p.bbits) && !getenv("HNSWB200_VIS_POW2");
+        snprintf(nm, sizeof nm, "hb::%s<%s dim %u,%s,ef<=%u>", generic_list ? "search_kernel" : "search_kernel_reg", qn, a.L.dim,
+                 !use16 ? "Vis32" : (u16n && !generic_list) ? "Vis16N" : "Vis16", generic_list ? a.ef : (a.ef <= 64 ? 64u : a.ef <= 128 ? 128u : 256u));
+        set_search_variant(nm);
+    }
     if (!generic_list) {
         // register-resident list: ef <= 64 / 128 / 256 -> 2 / 4 / 8 keys per lane
         const uint32_t rkpl = a.ef <= 64 ? 2 : a.ef <= 128 ? 4 : 8;
@@ -923,6 +909,67 @@ cudaError_t launch_topk_merge(const uint32_t* ids, const float* dists, uint32_t 
     cudaError_t e = cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     topk_merge_kernel<<<nq, 128, smem, st>>>(ids, dists, G, nq, k, P, out_ids, out_dists);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// Peer exchange over NVLink / NVSwitch without a collective library: a rank copies its result rows into the
+// gather buffers of the other ranks (peer memory mapped with hnswb200_ipc_open), then raises a flag word in each of
+// them; the consumer waits for the flags of all ranks before it merges.  Stream order makes the rows visible before
+// the flag: the signal kernel starts after the kernel that stored them has completed.
+// ---------------------------------------------------------------------------
+struct PeerPtrs { void* p[HB_MAX_PEERS]; };
+
+__global__ void __launch_bounds__(256) peer_put_kernel(const uint4* __restrict__ src, uint64_t n16, PeerPtrs dst, uint32_t n_peers) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+        const uint4 v = __ldg(src + i);
+        for (uint32_t g = 0; g < n_peers; ++g) reinterpret_cast<uint4*>(dst.p[g])[i] = v;
+    }
+}
+__global__ void peer_signal_kernel(PeerPtrs flags, uint32_t n_peers, uint32_t slot, uint32_t epoch) {
+    if (threadIdx.x < n_peers) {
+        __threadfence_system();
+        uint32_t* f = reinterpret_cast<uint32_t*>(flags.p[threadIdx.x]) + slot;
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(epoch) : "memory");
+    }
+}
+// flags[0..n) >= epoch (wrap-safe), or give up after ~10 s and raise *status = 2
+__global__ void peer_wait_kernel(const uint32_t* flags, uint32_t n, uint32_t epoch, uint32_t* status) {
+    if (threadIdx.x >= n) return;
+    const long long t0 = clock64();
+    while (true) {
+        uint32_t v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + threadIdx.x) : "memory");
+        if ((int32_t)(v - epoch) >= 0) break;
+        if (clock64() - t0 > 20000000000ll) {
+            if (status) *reinterpret_cast<volatile uint32_t*>(status) = 2u;
+            break;
+        }
+        __nanosleep(200);
+    }
+}
+
+cudaError_t launch_peer_put(const void* src, uint64_t bytes, uint32_t n_peers, void* const* dst, int num_sms, cudaStream_t st) {
+    if (!bytes || !n_peers) return cudaSuccess;
+    PeerPtrs pp{};
+    for (uint32_t g = 0; g < n_peers; ++g) pp.p[g] = dst[g];
+    const uint64_t n16 = bytes / 16;
+    uint64_t blocks = (n16 + 255) / 256;
+    if (blocks > (uint64_t)num_sms * 4) blocks = (uint64_t)num_sms * 4;
+    peer_put_kernel<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(src), n16, pp, n_peers);
+    return cudaGetLastError();
+}
+cudaError_t launch_peer_signal(uint32_t n_peers, uint32_t* const* flags, uint32_t slot, uint32_t epoch, cudaStream_t st) {
+    if (!n_peers) return cudaSuccess;
+    PeerPtrs pp{};
+    for (uint32_t g = 0; g < n_peers; ++g) pp.p[g] = flags[g];
+    peer_signal_kernel<<<1, 32, 0, st>>>(pp, n_peers, slot, epoch);
+    return cudaGetLastError();
+}
+cudaError_t launch_peer_wait(const uint32_t* flags, uint32_t n, uint32_t epoch, uint32_t* status, cudaStream_t st) {
+    if (!n) return cudaSuccess;
+    peer_wait_kernel<<<1, 32, 0, st>>>(flags, n, epoch, status);
     return cudaGetLastError();
 }
 

@@ -38,11 +38,16 @@ struct SearchLaunch {
     uint32_t* out_nbrs = nullptr;  // nq, may be null: neighbour ids read
     uint32_t* nan_any = nullptr;  // optional: set to 1 if any query holds a NaN
     uint32_t* peer_ids[HB_MAX_PEERS] = {};  // fused all-gather targets (device-visible peer buffers)
+    float* peer_dists[HB_MAX_PEERS] = {};   // optional distance rows next to the id rows (base shards)
     uint32_t n_peers = 0;
     uint64_t peer_row0 = 0;
+    uint32_t id_offset = 0;  // added to every returned id (global ids of a base shard)
     uint32_t* work_counter;  // device u32, zero on entry
     bool counter_is_fresh = false;  // true: the caller guarantees *work_counter == 0 (no memset is enqueued)
     bool overlap_previous = false;  // launch as programmatic dependent of the previous kernel in the stream
+    // optional global continuation of the visited set's exact spill list (search_fast.cuh): spill_cap ids per warp
+    uint32_t* spill_ws = nullptr;
+    uint32_t spill_cap = 0, spill_warps = 0;
 };
 
 // f32 rows -> lane-sliced records (+ optional flat codes/mins/deltas)
@@ -100,5 +105,12 @@ cudaError_t bf_tc_chunk(const uint8_t* base_rec, uint64_t n_base, const RecLayou
 // merge G sorted lists of k (ids/dists [G][nq][k]) into one list of k per query
 cudaError_t launch_topk_merge(const uint32_t* ids, const float* dists, uint32_t G, uint32_t nq,
                               uint32_t k, uint32_t* out_ids, float* out_dists, cudaStream_t st);
+
+// peer exchange (kernels.cu): copy rows into peer buffers, raise / await per-rank flag words
+cudaError_t launch_peer_put(const void* src, uint64_t bytes, uint32_t n_peers, void* const* dst, int num_sms, cudaStream_t st);
+cudaError_t launch_peer_signal(uint32_t n_peers, uint32_t* const* flags, uint32_t slot, uint32_t epoch, cudaStream_t st);
+cudaError_t launch_peer_wait(const uint32_t* flags, uint32_t n, uint32_t epoch, uint32_t* status, cudaStream_t st);
+// name of the kernel variant the last launch_search of this thread ran (search_fast.cu)
+const char* last_search_variant();
 
 }  // namespace hb

@@ -61,7 +61,9 @@ typedef struct hnswb200_params {
 typedef struct hnswb200_search_stats {
     uint32_t* hops;   /* expansions = iterations of the loop at searcher.rs:36-95 that did not break */
     uint32_t* evals;  /* dist2other calls: 1 (entry point) + every unvisited neighbour */
-    uint32_t* flags;  /* bit0: NaN in query (reference panics), bit1: visited-set overflow fallback used */
+    uint32_t* flags;  /* bit0: NaN in query (reference panics); bit1: the visited set could not record an id, answers stay
+                         exact through list membership but `evals` may over-count for this query; bit2: the exact spill
+                         list of the visited set was used (everything exact) */
     uint32_t* nbrs;   /* neighbour ids read = sum of degrees of the expanded nodes (roofline accounting) */
 } hnswb200_search_stats;
 
@@ -73,6 +75,14 @@ int hnswb200_ctx_create(int device, hnswb200_ctx** out);
 void hnswb200_ctx_destroy(hnswb200_ctx* ctx);
 /* run all later work of this context on an existing cudaStream_t (e.g. torch's current stream) */
 int hnswb200_ctx_set_stream(hnswb200_ctx* ctx, void* cuda_stream);
+/* Consecutive searches of one context may overlap on the device: a search is launched as the programmatic dependent
+ * of the search enqueued directly before it, so its blocks take over the SMs the previous batch's last queries leave
+ * idle (a search reads nothing a previous search writes).  On the context's own stream the library knows what precedes a
+ * search and does this by itself.  On an ADOPTED stream (hnswb200_ctx_set_stream) the caller may enqueue work the
+ * library cannot see, so overlap is off until the caller opts in with allow = 1 and thereby promises that the query
+ * buffer of a search is complete before the PREVIOUS search of this context was enqueued (no producer kernel between two
+ * searches).  No reference analogue (ann_by_vector is one synchronous call, hnsw/src/template.rs:306-335). */
+int hnswb200_ctx_set_overlap(hnswb200_ctx* ctx, int allow);
 int hnswb200_ctx_sync(hnswb200_ctx* ctx);
 int hnswb200_ctx_device(const hnswb200_ctx* ctx);
 /* HNSWB200_VEC_*: the reference chooses its vector type at compile time (`type VecType = QuantVec;`,
@@ -189,6 +199,10 @@ int hnswb200_search_dev(hnswb200_ctx* ctx, const hnswb200_index* ix, const float
                         uint32_t* d_out_counts, uint32_t* d_hops, uint32_t* d_evals, uint32_t* d_flags,
                         uint32_t* d_nbrs);
 
+/* name of the kernel variant the last search launched from the calling thread ran (diagnostics / bench labels);
+ * valid until the thread's next search */
+const char* hnswb200_last_search_variant(void);
+
 /* The same search with the all-gather of the results fused into it (query-sharded, replicated index): the id row of
  * query q is also stored to row row_offset + q of each of the n_peers (<= 8) buffers in peer_ids -- device pointers
  * valid on this context's device, typically the other ranks' result buffers opened with hnswb200_ipc_open, so the
@@ -197,6 +211,25 @@ int hnswb200_search_dev_gather(hnswb200_ctx* ctx, const hnswb200_index* ix, cons
                                uint32_t n, uint32_t ef, uint32_t* d_out_ids, float* d_out_dists,
                                uint32_t* d_out_counts, uint32_t n_peers, uint32_t* const* peer_ids,
                                uint64_t row_offset);
+/* Base-sharded index (one HNSW per GPU over its slice of the base; the reference's per-shard semantics are those of
+ * ann_by_vector, template.rs:306-335): the same search, with id_offset added to every returned id (global ids) and the
+ * (id, distance) rows of query q also stored to row row_offset + q of the peers' gather buffers [G][nq][n] -- typically
+ * row_offset = rank * nq -- so that hnswb200_topk_merge_dev can merge them once every rank has signalled. */
+int hnswb200_search_dev_shard(hnswb200_ctx* ctx, const hnswb200_index* ix, const float* d_queries, uint64_t nq,
+                              uint32_t n, uint32_t ef, uint32_t id_offset, uint32_t* d_out_ids, float* d_out_dists,
+                              uint32_t* d_out_counts, uint32_t n_peers, uint32_t* const* peer_ids,
+                              float* const* peer_dists, uint64_t row_offset);
+/* Peer exchange over NVLink / NVSwitch without a collective library, asynchronous on the context stream:
+ *  peer_put    copy `bytes` (multiple of 16) from d_src to each of the n_peers (<= 8) device-visible destinations;
+ *  peer_signal after everything enqueued before it on this stream has completed, store `epoch` to word `slot` of each
+ *              peer's flag array (release, system scope);
+ *  peer_wait   hold the stream until the n_slots (<= 32) words of d_flags are all >= epoch (acquire, system scope;
+ *              wrap-safe compare).  A wait of more than ~10 s raises an error that hnswb200_ctx_sync reports.
+ * Flag arrays and gather buffers are hnswb200_dev_alloc memory opened on the peers with hnswb200_ipc_open. */
+int hnswb200_peer_put_dev(hnswb200_ctx* ctx, const void* d_src, uint64_t bytes, uint32_t n_peers, void* const* peer_dst);
+int hnswb200_peer_signal_dev(hnswb200_ctx* ctx, uint32_t n_peers, uint32_t* const* peer_flags, uint32_t slot,
+                             uint32_t epoch);
+int hnswb200_peer_wait_dev(hnswb200_ctx* ctx, const uint32_t* d_flags, uint32_t n_slots, uint32_t epoch);
 /* device buffers that the other processes of the box can write: plain cudaMalloc memory (filled with 0xFF) and its
  * CUDA IPC handle (64 bytes); ipc_open maps a peer's buffer into this context's device with peer access enabled */
 int hnswb200_dev_alloc(hnswb200_ctx* ctx, uint64_t bytes, void** out);

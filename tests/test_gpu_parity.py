@@ -200,8 +200,9 @@ def test_search_synthetic(H, oracle, dim, n, m, efc):
     check_search(H, oracle, orc, queries, 3, 50)
 
 
-# {} = the default path (ef <= 64: 3584-entry visited table, 7 blocks per SM); VIS_POW2 = the 4096-entry table instead
-PATHS = [{}, {"HNSWB200_VIS_POW2": "1"}, {"HNSWB200_GENERAL_PATH": "1"}, {"HNSWB200_VIS32": "1"},
+# {} = the default path (ef <= 128, quantised records of dimension 50/96/100/128: csrc/search_fast.cuh);
+# NO_FAST = the round-1 register-list kernel (ef <= 64: 3584-entry visited table); VIS_POW2 = its 4096-entry table
+PATHS = [{}, {"HNSWB200_NO_FAST": "1"}, {"HNSWB200_VIS_POW2": "1"}, {"HNSWB200_GENERAL_PATH": "1"}, {"HNSWB200_VIS32": "1"},
          {"HNSWB200_GENERAL_PATH": "1", "HNSWB200_VIS32": "1"}]
 
 
@@ -701,19 +702,73 @@ def test_two_contexts_search_one_index_concurrently(H, oracle, glove, glove_inde
 
 
 def test_search_small_visited_table_under_heavy_load(H, oracle, monkeypatch):
-    """ef <= 64 runs on the 3584-entry visited table (7 blocks per SM).  Wide rows (M = 32) at ef = 64 fill it far beyond
-    its design load, so many probe windows run out: answers must stay identical to the oracle (list-membership fallback),
-    and identical to the 4096-entry table's."""
+    """Wide rows (M = 32) at ef = 64 fill the visited table far beyond its design load.  Default kernel (search_fast.cuh):
+    full buckets spill to the following ones and, after 8 of them, to the exact spill list, so ids, distances, hops AND
+    the evaluation counter equal the oracle's for EVERY query (searcher.rs:61-72 evaluates an id once), also with the
+    smallest table the kernel accepts.  Round-1 kernel (NO_FAST): answers identical, the counter may over-count where the
+    overflow flag is raised."""
+    from hnsw_rs_b200 import _ffi
     base = synth(20000, 100, 64, 31)
     queries = synth(300, 100, 64, 32)
     orc = oracle.Index(32, 64, 100).insert_bulk(base)
     ix = to_gpu(H, orc)
     oids, odists, ocounts, ohops, oevals = orc.search_batch(queries, 10, 64, threads=8)
-    ids, dists, counts, st = ix.ann_batch(queries, 10, 64, with_stats=True)
-    assert np.array_equal(ids, oids) and np.array_equal(bits(dists), bits(odists)) and np.array_equal(counts, ocounts)
-    assert np.array_equal(st["hops"], ohops)
-    clean = st["flags"] == 0
-    assert np.array_equal(st["evals"][clean], oevals[clean]) and (st["evals"] >= oevals).all()
-    monkeypatch.setenv("HNSWB200_VIS_POW2", "1")
-    ids2, dists2, counts2 = ix.ann_batch(queries, 10, 64)
-    assert np.array_equal(ids, ids2) and np.array_equal(bits(dists), bits(dists2))
+    spilled = 0
+    for nb in (None, "514"):
+        if nb:
+            monkeypatch.setenv("HNSWB200_FAST_NB", nb)
+        ids, dists, counts, st = ix.ann_batch(queries, 10, 64, with_stats=True)
+        assert "search_kernel_fast" in _ffi.last_search_variant()
+        assert np.array_equal(ids, oids) and np.array_equal(bits(dists), bits(odists)) and np.array_equal(counts, ocounts)
+        assert np.array_equal(st["hops"], ohops)
+        assert not (st["flags"] & 2).any()
+        assert np.array_equal(st["evals"], oevals)            # including the queries that used the spill list
+        spilled += int(((st["flags"] & 4) != 0).sum())
+    monkeypatch.delenv("HNSWB200_FAST_NB")
+    monkeypatch.setenv("HNSWB200_NO_FAST", "1")
+    ids1, dists1, counts1, st1 = ix.ann_batch(queries, 10, 64, with_stats=True)
+    assert "search_kernel_reg" in _ffi.last_search_variant()
+    assert np.array_equal(ids1, oids) and np.array_equal(bits(dists1), bits(odists)) and np.array_equal(st1["hops"], ohops)
+    clean = (st1["flags"] & 2) == 0
+    assert np.array_equal(st1["evals"][clean], oevals[clean]) and (st1["evals"] >= oevals).all()
+    print("queries that used the spill list:", spilled)
+
+
+@pytest.mark.parametrize("dim,m", [(100, 16), (128, 16), (96, 12), (50, 12)])
+def test_fast_kernel_matches_oracle_and_round1_kernel(H, oracle, monkeypatch, dim, m):
+    """The second-generation search kernel (csrc/search_fast.cuh; ef <= 128, dimensions 50 / 96 / 100 / 128) against the
+    oracle and against the round-1 kernel on the same index: ids, distance bits, counts, hops and evaluations."""
+    from hnsw_rs_b200 import _ffi
+    norm = dim != 128
+    base = synth(8000, dim, 64, 51, normalise=norm)
+    queries = synth(257, dim, 64, 52, normalise=norm)
+    orc = oracle.Index(m, 3 * m, dim).insert_bulk(base)
+    ix = to_gpu(H, orc)
+    for ef, n in ((1, 1), (7, 10), (57, 10), (64, 64), (65, 10), (100, 100), (128, 130)):
+        o = orc.search_batch(queries, n, ef, threads=8)
+        a = ix.ann_batch(queries, n, ef, with_stats=True)
+        assert "search_kernel_fast" in _ffi.last_search_variant(), _ffi.last_search_variant()
+        monkeypatch.setenv("HNSWB200_NO_FAST", "1")
+        b = ix.ann_batch(queries, n, ef, with_stats=True)
+        assert "search_kernel_fast" not in _ffi.last_search_variant()
+        monkeypatch.delenv("HNSWB200_NO_FAST")
+        for r in (a, b):
+            assert np.array_equal(r[0], o[0]) and np.array_equal(bits(r[1]), bits(o[1])) and np.array_equal(r[2], o[2]), ef
+            assert np.array_equal(r[3]["hops"], o[3]) and np.array_equal(r[3]["evals"], o[4]), ef
+        assert (a[3]["flags"] == 0).all()
+        c = ix.ann_batch(queries, n, ef)                      # the variant without counters (the one bench.py times)
+        assert np.array_equal(c[0], o[0]) and np.array_equal(bits(c[1]), bits(o[1])) and np.array_equal(c[2], o[2]), ef
+
+
+def test_fast_kernel_extreme_deltas(H, oracle):
+    """Records whose delta is >= 2^100 (or whose range overflows f32) take the separately-rounded multiply path of the
+    fast kernel's distance (FastQuery::partial): still bit-identical to the oracle."""
+    r = np.random.default_rng(77)
+    base = synth(3000, 100, 16, 61, normalise=False)
+    base[::7] *= np.float32(3.0e32)      # delta ~ 1e30..1e31 >= 2^100
+    base[5::11] *= np.float32(1.0e-30)   # tiny deltas
+    queries = synth(100, 100, 16, 62, normalise=False)
+    queries[::3] *= np.float32(3.0e32)
+    orc = oracle.Index(12, 36, 100).insert_bulk(base)
+    for ef in (10, 64, 100):
+        check_search(H, oracle, orc, queries, 10, ef)
