@@ -218,7 +218,11 @@ def main():
     ap.add_argument("--steps", type=int, default=100)  # 100 steps = 64 ms of kernels: long enough for the clock sampler
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n-base", type=int, default=1183514)
+    ap.add_argument("--config", default="c2", choices=["c2", "c3", "c4", "c5"],
+                    help="BASELINE.json configuration: c2 = the headline (configs[1]); c3 / c4 / c5 = configs[2..4], see "
+                         "bench_configs.py")
+    ap.add_argument("--shard-size", type=int, default=12500000, help="c5: rows per GPU shard")
+    ap.add_argument("--n-base", type=int, default=0, help="base rows (default: what the configuration names)")
     ap.add_argument("--n-queries", type=int, default=10000)
     ap.add_argument("--dim", type=int, default=100)
     ap.add_argument("--m", type=int, default=16)
@@ -233,6 +237,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the oracle timing (profiling helper)")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3)
+    if a.config == "c2" and not a.n_base:
+        a.n_base = 1183514
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -251,6 +257,7 @@ def main():
                          "(the reference arm also builds its index with the device builder)")
     torch.cuda.set_device(local_rank)
 
+    dist = None
     if world > 1 and a.impl == "b200":
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -259,6 +266,21 @@ def main():
     # adopted stream: consecutive searches may only overlap with our promise that nothing else is enqueued between them
     # (true for every loop below: the query buffers are written once, before the first search)
     ctx.set_overlap(True)
+
+    if a.config != "c2":
+        import bench_configs
+        if a.impl == "reference":
+            emit({"impl": "reference", "unavailable": "--impl reference is defined for the headline configuration (c2); "
+                  "c3/c4/c5 report the oracle as cpu_baseline inside their own line"})
+            return 0
+        env = {"torch": torch, "dist": dist if world > 1 else None, "H": H, "_ffi": _ffi, "ctx": ctx, "rank": rank,
+               "local_rank": local_rank, "world": world, "ROOT": ROOT, "emit": emit, "ClockSampler": ClockSampler,
+               "recall_at_k": recall_at_k, "alg_bytes": alg_bytes, "oracle_from_index": oracle_from_index, "synth": synth}
+        rc = bench_configs.run(a, env)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return rc
 
     workload = (f"C2 synthetic GloVe-100 shape: {a.n_base}x{a.dim} unit-norm clustered mixture ({a.ncent} centres, "
                 f"sigma 0.35, seed 1), {a.n_queries} queries/GPU (seed 2+rank), k={K}, " +

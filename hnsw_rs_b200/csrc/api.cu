@@ -84,19 +84,28 @@ int hnswb200_ctx_create(int device, hnswb200_ctx** out) {
     if (device < 0 || device >= count) return fail(HNSWB200_EINVAL, "ctx_create: bad device index");
     hnswb200_ctx* c = new hnswb200_ctx();
     c->device = device;
-    HB_CUDA(cudaSetDevice(device));
-    cudaDeviceProp prop;
-    HB_CUDA(cudaGetDeviceProperties(&prop, device));
-    c->num_sms = prop.multiProcessorCount;
-    HB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    c->own_stream = true;
-    HB_CUDA(cudaMalloc((void**)&c->d_scratch, 64 * sizeof(uint32_t)));
-    HB_CUDA(cudaMemset(c->d_scratch, 0, 64 * sizeof(uint32_t)));
-    HB_CUDA(cudaHostAlloc((void**)&c->h_status, 64, cudaHostAllocMapped));
-    HB_CUDA(cudaHostGetDevicePointer((void**)&c->d_status, c->h_status, 0));
-    c->h_status[0] = 0;
-    HB_CUDA(cudaMalloc((void**)&c->d_counters, hnswb200_ctx::COUNTER_RING * sizeof(uint32_t)));
-    HB_CUDA(cudaMemset(c->d_counters, 0, hnswb200_ctx::COUNTER_RING * sizeof(uint32_t)));
+    // any failure below releases what was allocated so far (hnswb200_ctx_destroy copes with a half-built context)
+    auto init = [&]() -> int {
+        HB_CUDA(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        HB_CUDA(cudaGetDeviceProperties(&prop, device));
+        c->num_sms = prop.multiProcessorCount;
+        HB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->own_stream = true;
+        HB_CUDA(cudaMalloc((void**)&c->d_scratch, 64 * sizeof(uint32_t)));
+        HB_CUDA(cudaMemset(c->d_scratch, 0, 64 * sizeof(uint32_t)));
+        HB_CUDA(cudaHostAlloc((void**)&c->h_status, 64, cudaHostAllocMapped));
+        HB_CUDA(cudaHostGetDevicePointer((void**)&c->d_status, c->h_status, 0));
+        c->h_status[0] = 0;
+        HB_CUDA(cudaMalloc((void**)&c->d_counters, hnswb200_ctx::COUNTER_RING * sizeof(uint32_t)));
+        HB_CUDA(cudaMemset(c->d_counters, 0, hnswb200_ctx::COUNTER_RING * sizeof(uint32_t)));
+        return 0;
+    };
+    const int rc = init();
+    if (rc) {
+        hnswb200_ctx_destroy(c);
+        return rc;
+    }
     *out = c;
     return 0;
 }
@@ -1429,15 +1438,30 @@ int hnswb200_index_save_dir(hnswb200_ctx* c, const hnswb200_index* ix, const cha
     return 0;
 }
 
+static int load_dir_impl(hnswb200_ctx* c, const char* dir, hnswb200_index** out);
+
 int hnswb200_index_load_dir(hnswb200_ctx* c, const char* dir, hnswb200_index** out) {
     if (!c || !dir || !out) return fail(HNSWB200_EINVAL, "load: NULL argument");
+    // nothing unwinds across the C boundary: a crafted header must not turn into std::bad_alloc / length_error
+    try {
+        return load_dir_impl(c, dir, out);
+    } catch (const std::bad_alloc&) {
+        return fail(HNSWB200_ENOMEM, "load: out of host memory (corrupt header?)");
+    } catch (const std::exception& e) {
+        return fail(HNSWB200_EIO, std::string("load: ") + e.what());
+    }
+}
+
+static int load_dir_impl(hnswb200_ctx* c, const char* dir, hnswb200_index** out) {
     std::string d(dir);
     struct stat st;
     if (stat(d.c_str(), &st) != 0) return fail(HNSWB200_EIO, "\"" + d + "\" does not exist");
     std::vector<uint8_t> b;
     if (!read_file(d + "/points", b) || b.size() < 16) return fail(HNSWB200_EIO, "Problem reading points file");
     uint64_t n = get_u64(&b[0]), psz = get_u64(&b[8]);
-    if (psz < 5 || b.size() < 16 + n * psz) return fail(HNSWB200_EIO, "points file is truncated");
+    // ids are < 2^31 and a point is at most 1 + 4*dim bytes: bound both before multiplying (no wrap-around)
+    if (psz < 5 || psz > (1ull << 24) || n >= (1ull << 31)) return fail(HNSWB200_EIO, "points file header is not plausible");
+    if ((b.size() - 16) / psz < n) return fail(HNSWB200_EIO, "points file is truncated");
     std::vector<uint8_t> pb;
     pb.swap(b);
     if (!read_file(d + "/params", b) || b.size() < 52) return fail(HNSWB200_EIO, "Problem reading params file");
@@ -1448,6 +1472,7 @@ int hnswb200_index_load_dir(hnswb200_ctx* c, const char* dir, hnswb200_index** o
     // The file does not name its VecType; the point size does: 1 + 8 + dim bytes for a QuantVec (quant.rs:91-93),
     // 1 + 4*dim for a FullVec (full.rs:45-47).  The two never coincide for an integer dim.
     const uint64_t dim = prm.dim;
+    if (dim == 0 || dim > (1ull << 22)) return fail(HNSWB200_EIO, "params.dim is not plausible");
     const bool full = psz == 1 + 4 * dim && psz != 9 + dim;
     if (!full && psz != 9 + dim) return fail(HNSWB200_EIO, "params.dim does not match the point size");
     std::vector<uint8_t> codes, levels(n);
@@ -1477,7 +1502,13 @@ int hnswb200_index_load_dir(hnswb200_ctx* c, const char* dir, hnswb200_index** o
     if (!dd) return fail(HNSWB200_EIO, "There was a problem reading layers");
     while (dirent* e = readdir(dd)) {
         if (e->d_name[0] == '.') continue;
-        idxs.push_back(strtoull(e->d_name, nullptr, 10));
+        char* end = nullptr;
+        const unsigned long long v = strtoull(e->d_name, &end, 10);
+        if (end == e->d_name || *end != '\0' || v > 255) {  // the reference parses the name as a number (template.rs:103-109); a level is one byte
+            closedir(dd);
+            return fail(HNSWB200_EIO, std::string("layers/") + e->d_name + ": not a layer file name");
+        }
+        idxs.push_back(v);
     }
     closedir(dd);
     std::sort(idxs.begin(), idxs.end());

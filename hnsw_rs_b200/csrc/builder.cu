@@ -431,16 +431,38 @@ static int ensure_weights(hnswb200_ctx* c, hnswb200_index* ix) {
 
 // Insert the (already stored) points new_ids: level classes from the top, ascending id
 // inside a class (template.rs:403-416 with the oracle's iteration convention).
+// Everything build_insert can refuse for reasons known up front (parameters, shared-memory working set), checked
+// BEFORE store_points mutates the index: a refused insert leaves the index exactly as it was.
+static int build_validate(const hnswb200_index* ix, uint64_t n_points_after) {
+    const hnswb200_params& prm = ix->params;
+    if (prm.ef_cons < prm.m)
+        return (set_error("build: ef_cons < m is not supported by the device build"), HNSWB200_EINVAL);
+    if (prm.m < 2) return (set_error("build: m must be >= 2"), HNSWB200_EINVAL);
+    BuildParams p{};
+    p.L = ix->points->L;
+    p.ef_cons = (uint32_t)prm.ef_cons;
+    p.m = (uint32_t)prm.m;
+    p.kpl = ((std::max<uint32_t>(p.ef_cons, p.m) + 31) / 32 + 1) / 2 * 2;
+    p.cand_cap = std::max<uint32_t>(256, 32 * p.kpl);
+    p.m_cap = (p.m + 1) / 2 * 2;
+    p.qd_cap = (p.L.dim + 7) / 8 * 8 + 8;
+    bool use16;
+    choose_visited(p.ef_cons, ix->graph->h.a0.S, n_points_after, &p.tbits, &p.bbits, &use16);
+    auto bytes = [&]() { return (use16 ? build_warp_smem<Vis16>(p) : build_warp_smem<Vis32>(p)) * BUILD_WPB; };
+    while (bytes() > 200 * 1024 && p.tbits > 9 && (!use16 || p.bbits <= p.tbits - 1 + 12)) --p.tbits;
+    if (bytes() > 227 * 1024) return (set_error("build: ef_cons too large for the shared-memory working set"), HNSWB200_EINVAL);
+    return 0;
+}
+
 int build_insert(hnswb200_ctx* c, hnswb200_index* ix, const std::vector<uint32_t>& new_ids, uint32_t batch) {
     if (new_ids.empty()) return 0;
     if (c->use()) return HNSWB200_ECUDA;
     hnswb200_graph* G = ix->graph;
     HostGraph& h = G->h;
     const hnswb200_params& prm = ix->params;
-    if (prm.ef_cons < prm.m)
-        return (set_error("build: ef_cons < m is not supported by the device build"), HNSWB200_EINVAL);
-    if (prm.m < 2) return (set_error("build: m must be >= 2"), HNSWB200_EINVAL);
-    int rc = ensure_weights(c, ix);
+    int rc = build_validate(ix, h.n_points());
+    if (rc) return rc;
+    rc = ensure_weights(c, ix);
     if (rc) return rc;
     std::vector<uint32_t> d0, du;
     rc = G->sync_new_nodes(*std::min_element(new_ids.begin(), new_ids.end()));
@@ -604,6 +626,8 @@ static int store_points(hnswb200_ctx* c, hnswb200_index* ix, const float* rows, 
                   ", but tried inserting points of dimension " + std::to_string(dim));
         return HNSWB200_EINVAL;
     }
+    int vrc = build_validate(ix, ix->graph->h.n_points() + n);
+    if (vrc) return vrc;
     std::vector<uint8_t> lv(n);
     if (levels) memcpy(lv.data(), levels, n);
     else draw_levels(ix->params.m, n, lv.data());  // re-seeded for every batch (points.rs:40)

@@ -172,6 +172,35 @@ class PeerGather:
             self._opened.append(p)
             ptrs.append(p.value)
         self.ptrs = (vp * self.world)(*ptrs)
+        # one flag word per rank (0xFF-filled = step -1), for signal_wait()
+        self.flag_local = vp()
+        check(lib().hnswb200_dev_alloc(ctx.h, 256, C.byref(self.flag_local)))
+        fh = (C.c_uint8 * 64)()
+        check(lib().hnswb200_ipc_export(ctx.h, self.flag_local, fh))
+        fhs = [None] * self.world
+        if self.world > 1:
+            dist.all_gather_object(fhs, bytes(fh), group=group)
+        fptrs = []
+        for r in range(self.world):
+            if r == self.rank:
+                fptrs.append(self.flag_local.value)
+                continue
+            p = vp()
+            check(lib().hnswb200_ipc_open(ctx.h, (C.c_uint8 * 64).from_buffer_copy(fhs[r]), C.byref(p)))
+            self._opened.append(p)
+            fptrs.append(p.value)
+        self.fptrs = (vp * self.world)(*fptrs)
+        self.step = 0
+        if self.world > 1:
+            dist.barrier(group=group)
+
+    def signal_wait(self):
+        """After search(): tell every rank this rank's rows of the step are stored, and hold the stream until the rows of
+        all ranks have arrived here (hnswb200_peer_signal_dev / _peer_wait_dev) -- no host synchronisation, no NCCL."""
+        from ._ffi import check, lib
+        self.step += 1
+        check(lib().hnswb200_peer_signal_dev(self.ctx.h, self.world, self.fptrs, self.rank, self.step))
+        check(lib().hnswb200_peer_wait_dev(self.ctx.h, self.flag_local, self.world, self.step))
 
     def search(self, index, d_queries_ptr, nq, ef, d_ids_ptr, d_dists_ptr=None, d_counts_ptr=None):
         """Asynchronous on the context's stream: search nq (<= rows_per_rank) device-resident queries, results to the
@@ -199,3 +228,138 @@ class PeerGather:
         if self.local:
             check(lib().hnswb200_dev_free(self.ctx.h, self.local))
             self.local = None
+        if getattr(self, "flag_local", None):
+            check(lib().hnswb200_dev_free(self.ctx.h, self.flag_local))
+            self.flag_local = None
+
+
+class PeerExchange:
+    """Device-resident all-gather + merge of per-rank top-k rows over peer memory -- the multi-GPU data path without a
+    collective library and without a host round trip (the numpy path above stays for the gloo tests).
+
+    Every rank owns two gather buffers [G][rows][k] (ids u32, distances f32; double-buffered by step parity) and one
+    flag word per rank, all plain device memory that the other ranks of the box map with CUDA IPC.  One step on rank r:
+      1. produce the local rows straight into slot r of the local buffer, and into slot r of every peer's buffer --
+         fused into the search kernel (hnswb200_search_dev_shard / _gather: peer stores over NVLink / NVSwitch while the
+         other queries compute), or with hnswb200_peer_put_dev after a brute force;
+      2. hnswb200_peer_signal_dev: store the step number to flag r of every rank (stream order: after the rows);
+      3. hnswb200_peer_wait_dev: hold the stream until all G flags of this rank have reached the step number;
+      4. hnswb200_topk_merge_dev (K6) over the G slots.
+    Everything is asynchronous on the context's stream.  A rank can run at most one step ahead of the slowest peer (its
+    step s+1 merge waits for every peer's step s+1 rows, which a peer produces only after its own step s merge), so two
+    buffers are enough."""
+
+    def __init__(self, ctx, rows, k, group=None):
+        import ctypes as C
+        from ._ffi import check, lib, vp
+        self.ctx, self.group, self.rows, self.k = ctx, group, int(rows), int(k)
+        self.rank, self.world = _world(group)
+        if self.world > 8:
+            raise ValueError("PeerExchange: at most 8 ranks (one box)")
+        self.slot_bytes = self.rows * self.k * 4
+        self.buf_bytes = self.world * self.slot_bytes            # one [G][rows][k] buffer
+        self.step = 0
+        self._local, self._opened = [], []
+
+        def shared(nbytes):
+            """allocate locally, exchange IPC handles, map the peers; returns the G base addresses (own one included)"""
+            p = vp()
+            check(lib().hnswb200_dev_alloc(ctx.h, nbytes, C.byref(p)))
+            self._local.append(p)
+            handle = (C.c_uint8 * 64)()
+            check(lib().hnswb200_ipc_export(ctx.h, p, handle))
+            handles = [bytes(handle)] * self.world
+            if self.world > 1:
+                _dist().all_gather_object(handles, bytes(handle), group=group)
+            out = []
+            for r in range(self.world):
+                if r == self.rank:
+                    out.append(p.value)
+                    continue
+                q = vp()
+                check(lib().hnswb200_ipc_open(ctx.h, (C.c_uint8 * 64).from_buffer_copy(handles[r]), C.byref(q)))
+                self._opened.append(q)
+                out.append(q.value)
+            return out
+
+        self.ids = shared(2 * self.buf_bytes)      # [2][G][rows][k] u32 on every rank
+        self.dists = shared(2 * self.buf_bytes)    # [2][G][rows][k] f32
+        # word r: last step rank r has completed.  dev_alloc fills with 0xFF = step -1 under the wrap-safe compare of
+        # hnswb200_peer_wait_dev, so no reset is needed
+        self.flags = shared(256)
+        if self.world > 1:
+            _dist().barrier(group=group)
+        self.others = [r for r in range(self.world) if r != self.rank]
+
+    # ---- addresses ----
+    def _slot(self, bases, rank_of_buffer, parity, slot):
+        return bases[rank_of_buffer] + parity * self.buf_bytes + slot * self.slot_bytes
+
+    def local_ids(self, parity=None):
+        """device address of this step's local [G][rows][k] id buffer"""
+        parity = self.step & 1 if parity is None else parity
+        return self.ids[self.rank] + parity * self.buf_bytes
+
+    def local_dists(self, parity=None):
+        parity = self.step & 1 if parity is None else parity
+        return self.dists[self.rank] + parity * self.buf_bytes
+
+    def _arr(self, values):
+        from ._ffi import vp
+        return (vp * max(1, len(values)))(*[vp(v) for v in values]) if values else (vp * 1)()
+
+    # ---- the four stages ----
+    def begin(self):
+        self.step += 1
+        return self.step & 1
+
+    def shard_search(self, index, d_queries_ptr, nq, ef, id_offset):
+        """stage 1 for a base-sharded HNSW (BASELINE config 5): rows of all nq queries, global ids"""
+        from ._ffi import check, lib
+        if nq != self.rows:
+            raise ValueError("PeerExchange.shard_search: nq must equal rows")
+        par = self.begin()
+        peer_ids = self._arr([self.ids[r] + par * self.buf_bytes for r in self.others])
+        peer_d = self._arr([self.dists[r] + par * self.buf_bytes for r in self.others])
+        check(lib().hnswb200_search_dev_shard(self.ctx.h, index.h, d_queries_ptr, nq, self.k, ef, id_offset,
+                                              self._slot(self.ids, self.rank, par, self.rank),
+                                              self._slot(self.dists, self.rank, par, self.rank), None,
+                                              len(self.others), peer_ids, peer_d, self.rank * self.rows))
+
+    def shard_bruteforce(self, points, d_queries_ptr, nq, id_offset):
+        """stage 1 for a base-sharded brute force (config 4): exact local top-k, then peer stores of the two row blocks"""
+        from ._ffi import check, lib
+        if nq != self.rows:
+            raise ValueError("PeerExchange.shard_bruteforce: nq must equal rows")
+        par = self.begin()
+        li, ld = self._slot(self.ids, self.rank, par, self.rank), self._slot(self.dists, self.rank, par, self.rank)
+        check(lib().hnswb200_bruteforce_topk_dev(self.ctx.h, points.h, d_queries_ptr, nq, self.k, id_offset, li, ld))
+        if self.others:
+            check(lib().hnswb200_peer_put_dev(self.ctx.h, li, self.slot_bytes, len(self.others),
+                                              self._arr([self._slot(self.ids, r, par, self.rank) for r in self.others])))
+            check(lib().hnswb200_peer_put_dev(self.ctx.h, ld, self.slot_bytes, len(self.others),
+                                              self._arr([self._slot(self.dists, r, par, self.rank) for r in self.others])))
+
+    def signal_wait(self):
+        """stages 2 + 3"""
+        from ._ffi import check, lib
+        flags = self._arr(self.flags)
+        check(lib().hnswb200_peer_signal_dev(self.ctx.h, self.world, flags, self.rank, self.step))
+        check(lib().hnswb200_peer_wait_dev(self.ctx.h, self.flags[self.rank], self.world, self.step))
+
+    def merge(self, d_out_ids_ptr, d_out_dists_ptr):
+        """stage 4: top-k of the G slots under (dist, id) (graph/src/dist.rs:30-37) for every row"""
+        from ._ffi import check, lib
+        check(lib().hnswb200_topk_merge_dev(self.ctx.h, self.local_ids(), self.local_dists(), self.world, self.rows, self.k,
+                                            d_out_ids_ptr, d_out_dists_ptr))
+
+    def close(self):
+        from ._ffi import check, lib
+        self.ctx.sync()
+        if self.world > 1:
+            _dist().barrier(group=self.group)
+        for p in self._opened:
+            check(lib().hnswb200_ipc_close(self.ctx.h, p))
+        for p in self._local:
+            check(lib().hnswb200_dev_free(self.ctx.h, p))
+        self._opened, self._local = [], []
