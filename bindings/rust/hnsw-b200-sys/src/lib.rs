@@ -158,3 +158,34 @@ extern "C" {
                                    k: u32, d_out_ids: *mut u32, d_out_dists: *mut f32) -> c_int;
     pub fn hnswb200_load_glove(path: *const c_char, lim: u64, out: *mut f32, cap: u64, dim_out: *mut u64) -> i64;
 }
+
+
+/// The process-wide default context (device 0) behind a mutex: a context serves one host thread at a time
+/// (INTEGRATION.md), so every safe wrapper goes through `engine::with_ctx`.
+pub mod engine {
+    use super::*;
+    use std::ffi::CStr;
+    use std::sync::{Mutex, OnceLock};
+
+    struct Ctx(*mut hnswb200_ctx);
+    unsafe impl Send for Ctx {}
+
+    static DEFAULT: OnceLock<Mutex<Ctx>> = OnceLock::new();
+
+    pub fn last_error() -> String {
+        unsafe { CStr::from_ptr(hnswb200_last_error()).to_string_lossy().into_owned() }
+    }
+    pub fn check(rc: c_int) -> Result<(), String> {
+        if rc == HNSWB200_OK { Ok(()) } else { Err(last_error()) }
+    }
+    /// Runs `f` with the default context locked.  Panics when there is no CUDA device: the engine has no CPU fallback.
+    pub fn with_ctx<R>(f: impl FnOnce(*mut hnswb200_ctx) -> R) -> R {
+        let m = DEFAULT.get_or_init(|| {
+            let mut c = std::ptr::null_mut();
+            check(unsafe { hnswb200_ctx_create(0, &mut c) }).expect("no CUDA device: this engine has no CPU fallback");
+            Mutex::new(Ctx(c))
+        });
+        let g = m.lock().unwrap_or_else(|e| e.into_inner());
+        f(g.0)
+    }
+}

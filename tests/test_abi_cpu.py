@@ -49,6 +49,51 @@ def test_rust_binding_declares_every_symbol():
     assert bound == set(declared_symbols())
 
 
+def test_rust_crates_resolve_the_reference_callers_imports():
+    """The `use` paths of the reference's own caller (eval_glove/src/main.rs:8-15) and the items its code touches
+    (:37-41 HNSW::new / insert_bulk / insert_vec / ann_by_vector, :104-105 get_point / get_vals) exist in the drop-in
+    crates under bindings/rust/ with the reference's crate names and module paths.  (Source-level check: there is no Rust
+    toolchain in this image.)"""
+    rs = os.path.join(ROOT, "bindings", "rust")
+
+    def src(*p):
+        return open(os.path.join(rs, *p)).read()
+
+    def crate_name(d):
+        return re.search(r'^name\s*=\s*"([^"]+)"', src(d, "Cargo.toml"), re.M).group(1)
+
+    for d in ("hnsw", "vectors", "points", "graph"):
+        assert crate_name(d) == d
+    # use hnsw::helpers::args::parse_args_eval; use hnsw::helpers::glove::load_glove_array; use hnsw::template::HNSW;
+    assert re.search(r"pub mod helpers;", src("hnsw", "src", "lib.rs")) and re.search(r"pub mod template;", src("hnsw", "src", "lib.rs"))
+    assert re.search(r"pub mod params;", src("hnsw", "src", "lib.rs"))
+    assert re.search(r"pub mod args;", src("hnsw", "src", "helpers.rs")) and re.search(r"pub mod glove;", src("hnsw", "src", "helpers.rs"))
+    assert re.search(r"pub fn parse_args_eval\(", src("hnsw", "src", "helpers", "args.rs"))
+    glove = src("hnsw", "src", "helpers", "glove.rs")
+    assert re.search(r"pub fn load_glove_array\(", glove) and re.search(r"pub fn brute_force_nns\(", glove)
+    tpl = src("hnsw", "src", "template.rs")
+    assert re.search(r"pub struct HNSW\b", tpl) and "pub params: Params" in tpl
+    for fn in ("new", "insert_bulk", "insert_vec", "ann_by_vector", "save", "load", "len", "distance", "get_point", "get_layer",
+               "layer_degrees", "assert_param_compliance"):
+        assert re.search(r"pub fn %s\(" % fn, tpl), fn
+    assert "unsafe impl Sync" not in tpl                      # ADVICE r1: the context sits behind a Mutex instead
+    assert "Mutex<Handles>" in tpl and "q.len() != dim" in tpl  # ... and ann_batch validates every query length
+    prm = src("hnsw", "src", "params.rs")
+    assert re.search(r"pub struct Params\b", prm) and all(re.search(r"pub fn %s\(" % f, prm) for f in ("from_m", "from_m_efcons", "from"))
+    # use vectors::VecBase;  (+ the items of SURVEY 8b)
+    vec = src("vectors", "src", "lib.rs")
+    assert re.search(r"pub trait VecBase\b", vec) and re.search(r"pub struct QuantVec\b", vec) and re.search(r"pub struct FullVec\b", vec)
+    for fn in ("new", "dim", "iter_vals", "distance", "dist2other", "dist2many", "get_vals"):
+        assert re.search(r"fn %s\b" % fn, vec), fn
+    assert re.search(r"pub trait Serializer\b", src("vectors", "src", "serializer.rs"))
+    pts = src("points", "src", "points.rs")
+    assert re.search(r"pub trait Points\b", pts) and re.search(r"pub struct SimplePoints\b", pts)
+    assert re.search(r"pub struct Point\b", src("points", "src", "point.rs"))
+    g = src("graph", "src", "lib.rs")
+    assert "pub type NodeID = u32" in g and re.search(r"pub struct Dist\b", g) and re.search(r"pub enum GraphError\b", g)
+    assert re.search(r"pub struct Graph\b", g) and re.search(r"pub fn neighbors_vec\(", g)
+
+
 def test_version_and_params_default(H):  # hnsw/src/params.rs:15-44
     from hnsw_rs_b200 import _ffi
     L = H.lib()

@@ -133,8 +133,9 @@ def test_sharded_two_gpus_nccl(oracle, tmp_path):
 
 # ---- device-resident exchange: peer stores + flag words + K6, no collective library in the data path -------------
 def _px_worker(rank, world, port, out_dir, ndev):
-    """Two ranks, gloo for the bootstrap only.  With one GPU both ranks share device 0 (CUDA IPC between processes works
-    on one device too), so this runs on the driver's 1-GPU lease; with more GPUs each rank takes its own."""
+    """Two ranks on two GPUs, gloo for the bootstrap only (no NCCL anywhere).  Never two ranks on ONE GPU: a kernel that
+    spins on a flag another process must raise is not guaranteed to run at the same time as that process's kernels
+    (B200_PROFILING.md: Xid 109)."""
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
@@ -214,6 +215,8 @@ def test_peer_exchange_two_ranks(oracle, tmp_path):
     import torch
     import torch.multiprocessing as mp
     ndev = torch.cuda.device_count()
+    if ndev < 2:
+        pytest.skip("needs 2 GPUs (ranks that wait for each other's flags must not share one GPU)")
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     mp.spawn(_px_worker, args=(2, port, str(tmp_path), ndev), nprocs=2, join=True)
     for r in range(2):
