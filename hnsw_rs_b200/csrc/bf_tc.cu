@@ -10,6 +10,13 @@
 // care about the order of its terms, so the permuted code bytes need no second copy of the base; only
 // the query side is copied once with its non-code bytes (min, delta, padding) zeroed.
 //
+// The query side is CENTRED: A holds (cq - 128) as s8 (code ^ 0x80), B the raw u8 record bytes, so the tensor core
+// delivers dotm = Sum (cq-128)*cb and x_i = (cq_i-128)*dq + xmid with xmid = mq + 128*dq (the value of code 128, near
+// the vector's mean).  In that form every term next to the dot product is small (no 128*Sum cb offsets that cancel), and
+// a whole group of 32 base columns can be rejected with ONE integer maximum against a per-(query, group) bound --
+// the float estimate below runs only for groups that may hold a survivor (round 1 ran it for every pair: 7
+// instructions per pair, tensor pipe 14 % busy).
+//
 // The algebraic value differs from the reference's separately rounded chain by a few 1e-7 relative to
 // Sum x^2 + Sum y^2, so it is used as a FILTER: a pair survives if its estimate is within a safety margin
 // of the query's current k-th exact distance; survivors (about k per query per doubling of the base) are
@@ -54,6 +61,8 @@ struct TcSmem {
     uint8_t b[TC_B_BYTES];              // 1024-aligned (swizzle atom)
     uint8_t a[TC_STAGES][TC_A_BYTES];
     float cu[TC_N], cv[TC_N], cw[TC_N], cb[TC_N];  // per-column constants
+    // per group of 32 columns: min Bc', [min, max] of v and w, max u (quick reject of the whole group)
+    float g_bmin[TC_N / 32], g_vmin[TC_N / 32], g_vmax[TC_N / 32], g_wmin[TC_N / 32], g_wmax[TC_N / 32], g_umax[TC_N / 32];
     unsigned long long b_full, a_full[TC_STAGES], a_empty[TC_STAGES], acc_full[2], acc_empty[2];
     uint32_t tmem_base;
 };
@@ -113,8 +122,12 @@ __device__ __forceinline__ uint64_t tc_smem_desc(const void* p) {
     const uint32_t hi = 64u | (1u << 14) | (2u << 29);
     return ((uint64_t)hi << 32) | lo;
 }
-// instruction descriptor: dense, D = s32, A = B = u8, both K-major, N = 256, M = 128
-constexpr uint32_t TC_IDESC = (2u << 4) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+// instruction descriptor: dense, D = s32 (bits 4-5 = 2), A = s8 (bits 7-9 = 1: the centred query codes), B = u8 (bits 10-12 = 0),
+// both K-major, N = 256, M = 128
+#ifndef HB_TC_CENTRED
+#define HB_TC_CENTRED 1
+#endif
+constexpr uint32_t TC_IDESC = (2u << 4) | (HB_TC_CENTRED ? (1u << 7) : 0u) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
 
 __device__ __forceinline__ u64 mul2(u64 a, u64 b) {
     u64 r;
@@ -167,6 +180,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bf_tc_filter_kernel(const __gri
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    if (warp >= 2 && warp < 2 + TC_N / 32) {  // aggregates of column group (warp - 2)
+        const int gidx = warp - 2, c = gidx * 32 + lane;
+        float bmin = S.cb[c], vmin = S.cv[c], vmax = vmin, wmin = S.cw[c], wmax = wmin, umax = S.cu[c];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            bmin = fminf(bmin, __shfl_xor_sync(HB_FULL, bmin, o));
+            vmin = fminf(vmin, __shfl_xor_sync(HB_FULL, vmin, o));
+            vmax = fmaxf(vmax, __shfl_xor_sync(HB_FULL, vmax, o));
+            wmin = fminf(wmin, __shfl_xor_sync(HB_FULL, wmin, o));
+            wmax = fmaxf(wmax, __shfl_xor_sync(HB_FULL, wmax, o));
+            umax = fmaxf(umax, __shfl_xor_sync(HB_FULL, umax, o));
+        }
+        if (lane == 0) {
+            S.g_bmin[gidx] = bmin; S.g_vmin[gidx] = vmin; S.g_vmax[gidx] = vmax;
+            S.g_wmin[gidx] = wmin; S.g_wmax[gidx] = wmax; S.g_umax[gidx] = umax;
+        }
+    }
+    __syncthreads();
     const uint32_t tmem = S.tmem_base;
 
     if (warp == 0) {
@@ -227,6 +258,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bf_tc_filter_kernel(const __gri
                       "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                     : "r"(tmem + ((uint32_t)(quarter * 32) << 16) + acc * TC_N + col0));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#if HB_TC_CENTRED
+                {
+                    // Quick reject of the whole group: val_c = base_c + (a3*u_c)*dot_c with a3*u_c <= 0, so
+                    // val_c >= base_lb - smax * max(dot_c, 0) >= base_lb - smax * max(maxdot, 0) for every column c of the
+                    // group, where base_lb bounds base_c = a0 + Bc' + a1*v + a2*w from below over the group's ranges and
+                    // smax = -a3 * umax.  A group whose bound stays clearly positive holds no survivor.
+                    int mx = (int)v[0];
+#pragma unroll
+                    for (int j = 1; j < 32; ++j) mx = max(mx, (int)v[j]);
+                    const int gi = col0 >> 5;
+                    const float t1 = fminf(qc.y * S.g_vmin[gi], qc.y * S.g_vmax[gi]);
+                    const float t2 = fminf(qc.z * S.g_wmin[gi], qc.z * S.g_wmax[gi]);
+                    const float base_lb = qc.x + S.g_bmin[gi] + t1 + t2;
+                    const float dterm = (-qc.w * S.g_umax[gi]) * (float)max(mx, 0);
+                    // slack: far above the rounding of these few operations, far below the margins of real rejections
+                    const float slack = 1e-4f * (fabsf(qc.x) + fabsf(S.g_bmin[gi]) + fabsf(t1) + fabsf(t2) + dterm);
+                    if (base_lb - dterm > slack) continue;  // NaN / -inf (non-finite parameters) fall through to the estimate
+                }
+#endif
                 float e[32];
                 float lo = INFINITY;
 #pragma unroll
@@ -313,7 +363,7 @@ __global__ void __launch_bounds__(256) bf_tc_base_consts_kernel(const uint8_t* _
     }
 }
 
-// masked copy of the query records (the A operand) + (dq, mq, Sq, Qc) per query
+// masked, centred copy of the query records (the A operand) + (dq, xmid, dq * Sum (cq - 128), Sum x^2) per query
 __global__ void __launch_bounds__(256) bf_tc_query_prep_kernel(const uint8_t* __restrict__ qrec, uint32_t nq, RecLayout L,
                                                                ByteMask m, uint8_t* amask, float4* qstat) {
     const int lane = threadIdx.x & 31;
@@ -323,9 +373,16 @@ __global__ void __launch_bounds__(256) bf_tc_query_prep_kernel(const uint8_t* __
         uint32_t wd;
         float s1, s2, mn, dl;
         record_stats(qrec + (size_t)q * L.stride, L, m, lane, wd, s1, s2, mn, dl);
-        reinterpret_cast<uint32_t*>(amask + (size_t)q * TC_K)[lane] = wd;
         const float sq = dl * s1;
-        if (lane == 0) qstat[q] = make_float4(dl, mn, sq, dl * dl * s2 + 2.0f * mn * sq + (float)L.dim * mn * mn);
+        const float qc = dl * dl * s2 + 2.0f * mn * sq + (float)L.dim * mn * mn;  // Sum x^2
+#if HB_TC_CENTRED
+        // A = (code - 128) as s8 on the code bytes, 0 elsewhere; x_i = (c_i - 128)*dl + xmid
+        reinterpret_cast<uint32_t*>(amask + (size_t)q * TC_K)[lane] = (wd ^ 0x80808080u) & m.w[lane];
+        if (lane == 0) qstat[q] = make_float4(dl, mn + 128.0f * dl, dl * (s1 - 128.0f * (float)L.dim), qc);
+#else
+        reinterpret_cast<uint32_t*>(amask + (size_t)q * TC_K)[lane] = wd;
+        if (lane == 0) qstat[q] = make_float4(dl, mn, sq, qc);
+#endif
     }
 }
 

@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(SEARCH_WPB * 32, MINB) search_kernel_fast(Sear
             continue;
         }
         Q q;
-        q.init(p.L, qd, gl);
+        q.init(p.L, qd, gl, reinterpret_cast<u64*>(wsm + FAST_OFF_QTAB), lane);
         SearchCounters cnt{0u, 0u, 0u, 0u};
         RegList<KPL> L;
         __syncwarp();  // every lane has copied its part of qd before the scratch area is reused
@@ -183,10 +183,10 @@ static cudaError_t launch_fast_s(const SearchParams& p, int num_sms, cudaStream_
 }
 
 #ifndef HB_FAST_MINB2
-#define HB_FAST_MINB2 7  // resident blocks per SM of the ef <= 64 variant
+#define HB_FAST_MINB2 8  // resident blocks per SM of the ef <= 64 variant (64 registers, 576 visited buckets)
 #endif
 #ifndef HB_FAST_MINB4
-#define HB_FAST_MINB4 6  // ef <= 128
+#define HB_FAST_MINB4 7  // ef <= 128 (70 registers, 704 visited buckets)
 #endif
 
 template <class Q>

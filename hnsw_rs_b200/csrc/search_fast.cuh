@@ -169,9 +169,22 @@ __device__ __noinline__ uint32_t vis_spill(uint32_t* spill, uint32_t* gspill, ui
 
 // Query of a compile-time dimension (8*NCH + REM, REM <= 4) in registers; evaluates one record per group of 4 lanes
 // and leaves the accumulators to the caller (no cross-lane sum here).
+#ifndef HB_FAST_QSMEM
+#define HB_FAST_QSMEM 1  // 1: the query's value pairs stay in shared memory (one LDS.64 per chunk) instead of 2*NCH registers:
+                         // -2 % at equal occupancy, but 64 registers and an eighth block per SM: +5 % (profiles/r02_ab_variants.txt)
+#endif
+#ifndef HB_FAST_PIPE
+#define HB_FAST_PIPE 0   // 1: the record of the next round is loaded before the current one is evaluated
+#endif
+#ifndef HB_FAST_ROWPF
+#define HB_FAST_ROWPF 1  // 1: the adjacency row of every admitted key is requested (L2) at admission
+#endif
+constexpr uint32_t FAST_QS_BYTES = HB_FAST_QSMEM ? 16 * 32 + 0 : 0;  // up to 16 chunks x 4 lanes x 8 bytes
+
 template <int NCH, int REM>
 struct FastQuery {
     static_assert(REM <= 4, "one remainder element per lane of a group");
+    static_assert(NCH <= 16, "shared-memory query area holds 16 chunks");
     using RQ = RegQuery<NCH, REM>;
     static constexpr int W = RQ::W;
     static constexpr int TAIL = RQ::TAIL;
@@ -180,16 +193,33 @@ struct FastQuery {
     // remainder bytes: tail form -> bytes 8..11 of the tail word; compact form -> lane 0's slice positions 2*NCH + r
     static constexpr int RP0 = TAIL ? 8 : 2 * NCH;             // slice position (or tail byte) of remainder element 0
     static constexpr bool STRADDLE = REM > 0 && (RP0 % 4) + REM > 4;  // the REM bytes span two 32-bit words
+#if HB_FAST_QSMEM
+    const u64* qs;    // this lane's column of the [chunk][lane of group] table in shared memory
+    __device__ __forceinline__ u64 qk(int k) const { return qs[4 * k]; }
+#else
     u64 q[NCH ? NCH : 1];
+    __device__ __forceinline__ u64 qk(int k) const { return q[k]; }
+#endif
     float qrem;       // query value of remainder element gl (lanes gl >= REM: 0)
     u64 nz;
 
-    __device__ __forceinline__ void init(const RecLayout&, const float* qd, int gl) {
+    // qd: the dequantised query in shared memory (natural order); qtab: FAST_QS_BYTES of shared memory that stay valid
+    // for the whole query (only used when the query lives in shared memory)
+    __device__ __forceinline__ void init(const RecLayout&, const float* qd, int gl, u64* qtab, int lane) {
+#if HB_FAST_QSMEM
+        for (int i = lane; i < 4 * NCH; i += 32) {  // entry (k, l) = values 8k+2l, 8k+2l+1
+            const int k = i >> 2, l = i & 3;
+            float2 v = *reinterpret_cast<const float2*>(qd + 8 * k + 2 * l);
+            qtab[i] = pk(v.x, v.y);
+        }
+        qs = qtab + gl;
+#else
 #pragma unroll
         for (int k = 0; k < NCH; ++k) {
             float2 v = *reinterpret_cast<const float2*>(qd + 8 * k + 2 * gl);
             q[k] = pk(v.x, v.y);
         }
+#endif
         qrem = (REM > 0 && gl < REM) ? qd[8 * NCH + gl] : 0.0f;
         nz = hb_negzero2;
     }
@@ -230,7 +260,7 @@ struct FastQuery {
 #pragma unroll
             for (int k = 0; k < NCH; ++k) {
                 const int j = k / 8, c = k % 8;
-                acc = chunk_acc(acc, word32(w[j], c / 2), (c & 1) * 2, dl, mn2, q[k]);
+                acc = chunk_acc(acc, word32(w[j], c / 2), (c & 1) * 2, dl, mn2, qk(k));
             }
             if (REM > 0) {
                 const float fm = __uint_as_float(__byte_perm(rw, 0x4B000000u, remsel));
@@ -243,7 +273,7 @@ struct FastQuery {
 #pragma unroll
             for (int k = 0; k < NCH; ++k) {
                 const u64 m2 = pk(RQ::slice_magic(w, 2 * k), RQ::slice_magic(w, 2 * k + 1));
-                acc = add2(acc, chunk_sq(m2, dl2, nmd2, mn2, q[k], nz));
+                acc = add2(acc, chunk_sq(m2, dl2, nmd2, mn2, qk(k), nz));
             }
             if (REM > 0) {
                 // one remainder element per lane; the second half of the packed pair is a dummy (code 0 against 0)
@@ -259,7 +289,91 @@ struct FastQuery {
 
 // per warp (wsm, 16-byte aligned): 32 candidate ids | spill list | worst key | scratch | visited buckets
 constexpr uint32_t FAST_OFF_SPILL = 128, FAST_OFF_WORST = FAST_OFF_SPILL + FAST_SPILL * 4, FAST_OFF_SCRATCH = FAST_OFF_WORST + 16,
-                   FAST_OFF_TABLE = FAST_OFF_SCRATCH + FAST_SCRATCH_BYTES;
+                   FAST_OFF_QTAB = FAST_OFF_SCRATCH + FAST_SCRATCH_BYTES, FAST_OFF_TABLE = FAST_OFF_QTAB + FAST_QS_BYTES;
+
+#ifndef HB_FAST_SPEC
+#define HB_FAST_SPEC 0  // (measured: -5 %) load the adjacency row of the probable next expansion one hop ahead and prefetch its records
+#endif
+#ifndef HB_FAST_MERGE
+#define HB_FAST_MERGE 1  // 1: merge_ranked below; 0: RegList::merge (round 1)
+#endif
+
+// candidates.first() without popping: the id of the first entry whose "expanded" bit is clear
+template <int KPL>
+__device__ __forceinline__ bool list_peek(const RegList<KPL>& L, uint32_t& cid) {
+    uint32_t pick = 0xFFFFFFFFu;
+#pragma unroll
+    for (int s = KPL - 1; s >= 0; --s) {
+        const uint32_t lo = (uint32_t)L.v[s];
+        pick = (lo & 1u) ? pick : lo;
+    }
+    const unsigned m = __ballot_sync(HB_FULL, !(pick & 1u));
+    if (!m) return false;
+    cid = __shfl_sync(HB_FULL, pick, __ffs(m) - 1) >> 1;
+    return true;
+}
+
+// selected <- ef smallest of (selected U new keys): the same result as RegList::merge (and as the reference's one-by-one
+// admission, searcher.rs:74-94), with the work arranged so that nothing but the rank among the NEW keys loops over them:
+//   * the sorted list is dumped to shared memory once (one 16-byte store per lane); every lane that holds a new key
+//     finds its rank in it by a branch-free binary search (log2(32*KPL) steps);
+//   * rank among the new keys: one pass over the m compacted new keys (the only O(m) part, 7 instructions per key);
+//   * a new key's final position is the sum of its two ranks; an OR-reduction (REDUX) of those positions gives the
+//     occupancy mask of the merged list, and every list slot then knows whether it takes a new key (the c-th smallest,
+//     c = occupied positions below it) or the old key c places to its left.
+// key/want: this lane's new key; am = ballot(want); obuf: 32*KPL keys, kbuf and sbuf: 32 keys each.
+template <int KPL>
+__device__ __forceinline__ void merge_ranked(RegList<KPL>& L, u64 key, bool want, unsigned am, u64* obuf, u64* kbuf, u64* sbuf,
+                                             int& len, int ef, int lane, u64* worst_p) {
+    constexpr int C = 32 * KPL;
+    const int m = __popc(am);
+    // old list -> shared memory (position lane*KPL + s), compacted new keys -> kbuf
+#pragma unroll
+    for (int s = 0; s < KPL; s += 2)
+        *reinterpret_cast<ulonglong2*>(obuf + lane * KPL + s) = make_ulonglong2(L.v[s], L.v[s + 1]);
+    if (want) kbuf[__popc(am & ((1u << lane) - 1u))] = key;
+    __syncwarp();
+    // rank in the old list: number of list keys below `key` (the list ends in sentinels or the key is below list[ef-1],
+    // so the rank is at most C - 1 and C/2 + ... + 1 steps reach it)
+    int rl = 0;
+#pragma unroll
+    for (int st = C / 2; st >= 1; st >>= 1) rl += (obuf[rl + st - 1] < key) ? st : 0;
+    // rank among the new keys
+    int rn = 0;
+#pragma unroll 1
+    for (int j = 0; j < m; ++j) rn += (kbuf[j] < key) ? 1 : 0;
+    const int pos = rl + rn;
+    if (want) sbuf[rn] = key;  // the new keys in ascending order
+    // occupancy of the merged list by new keys, one word per 32 positions
+    uint32_t occ[KPL];
+#pragma unroll
+    for (int w = 0; w < KPL; ++w)
+        occ[w] = __reduce_or_sync(HB_FULL, (want && (pos >> 5) == w) ? (1u << (pos & 31)) : 0u);
+    __syncwarp();
+    const int newlen = min(ef, len + m);
+    // this lane's KPL slots lie in one word of the mask
+    const int q0 = lane * KPL, wq = q0 >> 5;
+    uint32_t mine = occ[0];
+    int below = 0;
+#pragma unroll
+    for (int w = 1; w < KPL; ++w) {
+        below += (w <= wq) ? __popc(occ[w - 1]) : 0;
+        mine = (w == wq) ? occ[w] : mine;
+    }
+    int c = below + __popc(mine & ((1u << (q0 & 31)) - 1u));
+#pragma unroll
+    for (int s = 0; s < KPL; ++s) {
+        const int q = q0 + s;
+        const bool isn = (mine >> (q & 31)) & 1u;
+        u64 v = isn ? sbuf[c] : obuf[q - c];
+        v = q < newlen ? v : RSENT;
+        L.v[s] = v;
+        if (q == ef - 1 && newlen == ef) *worst_p = v;  // the new admission bound (it stays the sentinel while |selected| < ef)
+        c += isn ? 1 : 0;
+    }
+    len = newlen;
+    __syncwarp();
+}
 
 // One whole query.  On exit L holds the <= ef nearest evaluated nodes of layer 0, sorted.
 // gspill / gcap: this warp's slice of the global continuation of the spill list (may be null / 0).
@@ -276,10 +390,12 @@ __device__ __forceinline__ void search_query_fast(const Q& query, const uint8_t*
     const int gl = lane & 3, gbase = lane & ~3, grp = lane >> 2;
     const unsigned lt = (1u << lane) - 1u;
     float* accbuf = scratch;
-    u64* kbuf = reinterpret_cast<u64*>(scratch);
-    u64* mbuf = kbuf + 32;
+    // merge scratch (aliases the accumulators): old list | compacted new keys | sorted new keys
+    u64* obuf = reinterpret_cast<u64*>(scratch);
+    u64* kbuf = obuf + 32 * KPL;
+    u64* sbuf = kbuf + 32;
+    static_assert((32 * KPL + 64) * 8 <= FAST_SCRATCH_BYTES, "merge scratch does not fit");
     uint32_t layer = n_layers - 1;
-    int ef_l = layer ? 1 : ef;
     int len = 0;  // |selected|
     L.reset();
     if (lane == 0) *worst_p = RSENT;
@@ -287,16 +403,21 @@ __device__ __forceinline__ void search_query_fast(const Q& query, const uint8_t*
     // boot batch: the entry point (selected <- {Dist(ep, d)}, template.rs:316-319)
     uint32_t nb = lane == 0 ? ep : EMPTY_ID;
     bool seed = false;
+    bool fresh_row = false;  // nb was just loaded for a popped candidate and its records have not been requested yet
     uint32_t row = EMPTY_ID, next = EMPTY_ID, b0 = 0;
-    uint32_t S = layer ? g.SU : g.S0;
-    const uint32_t* adj = layer ? g.upper_adj : g.adj0;
+    // speculation: spec_nb = this lane's slot of the adjacency row of spec_id, the probable next expansion
+    uint32_t spec_id = EMPTY_ID, spec_nb = EMPTY_ID;
+    bool spec_pending = false;  // the records of spec_nb's row are still to be requested
 #pragma unroll 1
     while (true) {
+        const int ef_l = layer ? 1 : ef;
         // ---- one batch of up to 32 ids: results.insert_visited(node) (results.rs:101-103) ----
         const bool valid = !(nb & CHAIN_BIT);  // EMPTY_ID and chain markers carry bit 31
 #if HB_FAST_PREFETCH_ALL
-        if (valid) prefetch_record(rec + (size_t)nb * rec_stride, rec_stride);
+        // request the record of every neighbour before the visited test (unless that happened a hop ago: speculation hit)
+        if (fresh_row && valid) prefetch_record(rec + (size_t)nb * rec_stride, rec_stride);
 #endif
+        fresh_row = false;
         bool ovf;
         bool isnew = vis.insert_warp(nb, valid, ovf);
         if (__any_sync(HB_FULL, ovf)) {  // rare: 8 full buckets in a row
@@ -308,6 +429,14 @@ __device__ __forceinline__ void search_query_fast(const Q& query, const uint8_t*
         isnew = isnew && !seed;
         const unsigned nm = __ballot_sync(HB_FULL, isnew);
         const int ncnt = __popc(nm);
+#if HB_FAST_SPEC
+        if (spec_pending) {
+            // the row of the probable next expansion has arrived by now (it was requested at the pop): request the records
+            // of its neighbours a whole hop before they are evaluated
+            if (!(spec_nb & CHAIN_BIT)) prefetch_record(rec + (size_t)spec_nb * rec_stride, rec_stride);
+            spec_pending = false;
+        }
+#endif
         if (ncnt) {
             if (STATS) cnt.evals += ncnt;
             if (isnew) {
@@ -318,6 +447,35 @@ __device__ __forceinline__ void search_query_fast(const Q& query, const uint8_t*
 #endif
             }
             __syncwarp();
+#if HB_FAST_PIPE
+            {
+                // two record buffers: the loads of round r+1 are in flight while round r is evaluated
+                auto rec_of = [&](int r0) {
+                    const int idx = r0 + grp;
+                    return Q::load(rec + (size_t)newbuf[idx < ncnt ? idx : 0] * rec_stride, gl);
+                };
+                auto eval = [&](const typename Q::Rec& R, int r0) {
+                    const int idx = r0 + grp;
+                    u64 acc;
+                    float rsq;
+                    query.partial(R, gl, gbase, acc, rsq);
+                    *reinterpret_cast<u64*>(accbuf + idx * FAST_ACC_STRIDE + 2 * gl) = acc;
+                    if (Q::kRem > 0) accbuf[idx * FAST_ACC_STRIDE + 8 + gl] = rsq;
+                };
+                typename Q::Rec A = rec_of(0), B;
+#pragma unroll 1
+                for (int r0 = 0;; r0 += 16) {
+                    const bool moreB = r0 + 8 < ncnt;
+                    if (moreB) B = rec_of(r0 + 8);
+                    eval(A, r0);
+                    if (!moreB) break;
+                    const bool moreA = r0 + 16 < ncnt;
+                    if (moreA) A = rec_of(r0 + 16);
+                    eval(B, r0 + 8);
+                    if (!moreA) break;
+                }
+            }
+#else
 #pragma unroll 1
             for (int r0 = 0; r0 < ncnt; r0 += 8) {
                 const int idx = r0 + grp;
@@ -329,6 +487,7 @@ __device__ __forceinline__ void search_query_fast(const Q& query, const uint8_t*
                 *reinterpret_cast<u64*>(accbuf + idx * FAST_ACC_STRIDE + 2 * gl) = acc;
                 if (Q::kRem > 0) accbuf[idx * FAST_ACC_STRIDE + 8 + gl] = rsq;
             }
+#endif
             __syncwarp();
             // lane i: candidate i.  acc[0] takes the remainder squares in order (quant.rs:31-35), then
             // acc.iter().sum() left to right (quant.rs:36) and the square root
@@ -357,22 +516,32 @@ __device__ __forceinline__ void search_query_fast(const Q& query, const uint8_t*
             // later, nearer key would have evicted it one by one.
             const bool want = lane < ncnt && key < *worst_p;
             const unsigned am = __ballot_sync(HB_FULL, want);
+#if HB_FAST_ROWPF
+            // an admitted key may be expanded a few hops from now: request its adjacency row (layer 0) today
+            if (want && layer == 0) prefetch_l2(g.adj0 + (size_t)newbuf[lane] * g.S0);
+#endif
             if (am) {
+                __syncwarp();  // every lane has read its accumulators: the merge scratch may overwrite them
+#if HB_FAST_MERGE
+                merge_ranked<KPL>(L, key, want, am, obuf, kbuf, sbuf, len, ef_l, lane, worst_p);
+#else
                 const int kcnt = __popc(am);
-                __syncwarp();  // every lane has read its accumulators: the key buffer may overwrite them
                 if (want) kbuf[__popc(am & lt)] = key;
                 __syncwarp();
-                L.merge(kbuf, kcnt, mbuf, len, ef_l, lane);
-                if (lane == 0) *worst_p = len == ef_l ? mbuf[ef_l - 1] : RSENT;
+                L.merge(kbuf, kcnt, obuf, len, ef_l, lane);
+                if (lane == 0) *worst_p = len == ef_l ? obuf[ef_l - 1] : RSENT;
                 __syncwarp();
+#endif
             }
         }
         // ---- next batch ----
+        const uint32_t S = layer ? g.SU : g.S0;
         if (row != EMPTY_ID) {  // more of the current adjacency row (rows wider than 32, continuation rows)
             b0 += 32;
             if (b0 >= S) { row = next; next = EMPTY_ID; b0 = 0; }
         }
         seed = false;
+        bool have_nb = false;
         if (row == EMPTY_ID) {
             uint32_t cid;
             if (!L.pop(cid, lane)) {
@@ -380,11 +549,9 @@ __device__ __forceinline__ void search_query_fast(const Q& query, const uint8_t*
                 L.clear_flags();
                 if (layer == 0) break;
                 --layer;
-                S = layer ? g.SU : g.S0;
-                adj = layer ? g.upper_adj : g.adj0;
-                ef_l = layer ? 1 : ef;
                 {
-                    const u64 w = len == ef_l ? L.get(ef_l - 1) : RSENT;
+                    const int efn = layer ? 1 : ef;
+                    const u64 w = len == efn ? L.get(efn - 1) : RSENT;
                     if (lane == 0) *worst_p = w;
                 }
                 vis.clear(lane);
@@ -397,11 +564,32 @@ __device__ __forceinline__ void search_query_fast(const Q& query, const uint8_t*
             if (STATS) cnt.hops++;
             // layer.neighbors_vec(cid)  (graph/src/graph.rs:103-113) as fixed-stride rows
             row = layer ? __ldg(g.upper_off + cid) + (layer - 1) : cid;
+#if HB_FAST_SPEC
+            if (layer == 0) {
+                if (cid == spec_id) {  // the guess of the previous hop was right: its row is already here
+                    nb = spec_nb;
+                    have_nb = true;
+                }
+                // guess the next expansion: the best entry that is still unexpanded.  The reference pops exactly that one
+                // next unless this batch admits a nearer key (searcher.rs:36-44); a wrong guess costs one row load.
+                uint32_t c2;
+                spec_id = EMPTY_ID;
+                if (list_peek<KPL>(L, c2)) {
+                    spec_id = c2;
+                    spec_nb = ((uint32_t)lane < g.S0) ? __ldg(g.adj0 + (size_t)c2 * g.S0 + lane) : EMPTY_ID;
+                    spec_pending = true;
+                }
+            }
+#endif
         }
-        {
+        if (!have_nb) {
+            const uint32_t* adj = layer ? g.upper_adj : g.adj0;
             const uint32_t* rp = adj + (size_t)row * S;
             const uint32_t i = b0 + lane;
             nb = (i < S) ? __ldg(rp + i) : EMPTY_ID;
+            fresh_row = true;
+        }
+        {
             const bool ok = !(nb & CHAIN_BIT);
             const unsigned mk = __ballot_sync(HB_FULL, !ok && nb != EMPTY_ID);
             if (mk) next = __shfl_sync(HB_FULL, nb, __ffs(mk) - 1) & ~CHAIN_BIT;
