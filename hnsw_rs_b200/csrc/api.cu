@@ -1201,6 +1201,7 @@ int hnswb200_bruteforce_topk_dev(hnswb200_ctx* c, const hnswb200_points* base, c
                  o_buf = cv.take(nq * (size_t)cap * 8), o_cnt = cv.take(nq * 4),
                  o_bconst = cv.take(use_tc ? N * 16 : 0), o_qstat = cv.take(use_tc ? nq * 16 : 0),
                  o_qconst = cv.take(use_tc ? nq_pad * 16 : 0), o_amask = cv.take(use_tc ? nq_pad * 128 : 0),
+                 o_qshift = cv.take(use_tc ? nq_pad * 4 : 0),
                  o_qnorm = cv.take(base->metric == HNSWB200_METRIC_COSINE ? nq * L.dim * 4 : 0);
     if (c->bf_ws_reserve(cv.off)) return HNSWB200_ECUDA;
     unsigned char* W = (unsigned char*)c->d_bf_ws;
@@ -1232,7 +1233,8 @@ int hnswb200_bruteforce_topk_dev(hnswb200_ctx* c, const hnswb200_points* base, c
     // per-query buffer (adversarial order) is redone in pieces of `cap` rows, which cannot overflow.
     if (use_tc) {
         HB_CUDA(cudaMemsetAsync(amask.p, 0, nq_pad * 128, c->stream));
-        HB_CUDA(bf_tc_prepare(base->d_rec, N, L, qrec.p, (uint32_t)nq, bconst.p, amask.p, qstat.p, c->stream));
+        HB_CUDA(cudaMemsetAsync(W + o_qshift, 0, nq_pad * 4, c->stream));
+        HB_CUDA(bf_tc_prepare(base->d_rec, N, L, qrec.p, (uint32_t)nq, bconst.p, amask.p, qstat.p, (int*)(W + o_qshift), c->stream));
     }
     uint64_t done = 0;
     while (done < N) {
@@ -1242,7 +1244,7 @@ int hnswb200_bruteforce_topk_dev(hnswb200_ctx* c, const hnswb200_points* base, c
         uint64_t ch = done == 0 ? std::min<uint64_t>(use_tc ? first : cap, N) : std::min<uint64_t>(std::min<uint64_t>(done, MAXCH), N - done);
         if (use_tc && done > 0)
             HB_CUDA(bf_tc_chunk(base->d_rec, N, L, done, done + ch, id_offset, qrec.p, amask.p, qstat.p, bconst.p, qconst.p,
-                                (uint32_t)nq, reinterpret_cast<const unsigned long long*>(tau.p),
+                                (const int*)(W + o_qshift), (uint32_t)nq, reinterpret_cast<const unsigned long long*>(tau.p),
                                 reinterpret_cast<unsigned long long*>(buf.p), cap, cnt.p, ovf_flag, c->num_sms, c->stream));
         else
             HB_CUDA(launch_bf_chunk(base->d_rec, L, done, done + ch, id_offset, qrec.p, (uint32_t)nq, tau.p, buf.p,

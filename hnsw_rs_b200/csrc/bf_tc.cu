@@ -10,12 +10,16 @@
 // care about the order of its terms, so the permuted code bytes need no second copy of the base; only
 // the query side is copied once with its non-code bytes (min, delta, padding) zeroed.
 //
-// The query side is CENTRED: A holds (cq - 128) as s8 (code ^ 0x80), B the raw u8 record bytes, so the tensor core
-// delivers dotm = Sum (cq-128)*cb and x_i = (cq_i-128)*dq + xmid with xmid = mq + 128*dq (the value of code 128, near
-// the vector's mean).  In that form every term next to the dot product is small (no 128*Sum cb offsets that cancel), and
-// a whole group of 32 base columns can be rejected with ONE integer maximum against a per-(query, group) bound --
-// the float estimate below runs only for groups that may hold a survivor (round 1 ran it for every pair: 7
-// instructions per pair, tensor pipe 14 % busy).
+// (Experiment, compiled with -DHB_TC_CENTRED=1, off by default -- see the note at HB_TC_CENTRED below.)
+// Both sides are CENTRED at code 128: A holds (cq - 128) as s8 (code ^ 0x80), B the raw u8 record bytes, so the tensor
+// core delivers dotm = Sum (cq-128)*cb, and the epilogue subtracts the per-query integer 128 * Sum (cq-128) to get
+// dot'' = Sum (cq-128)*(cb-128) exactly.  With x_i = (cq_i-128)*dq + xmid, y_i = (cb_i-128)*db + ymid (xmid, ymid: the
+// values of code 128, near the vectors' means)
+//     d^2 = Sum x^2 + Sum y^2 - 2 (dq*db*dot'' + xmid * P + ymid * Sum x),      P = db * Sum (cb-128)
+// every term next to the dot product is small (no large offsets that cancel against each other), so a whole group of
+// 32 base columns can be rejected with ONE integer maximum against a per-(query, group) bound -- the float estimate
+// runs only for groups that may hold a survivor (round 1 ran it for every pair: 7 instructions per pair, tensor pipe
+// 14 % busy).
 //
 // The algebraic value differs from the reference's separately rounded chain by a few 1e-7 relative to
 // Sum x^2 + Sum y^2, so it is used as a FILTER: a pair survives if its estimate is within a safety margin
@@ -54,6 +58,7 @@ constexpr int TC_COLS_PER_WARP = TC_N / (TC_EPI_WARPS / 4);
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr uint32_t TC_A_BYTES = TC_M * TC_K;  // 16 KB
 constexpr uint32_t TC_B_BYTES = TC_N * TC_K;  // 32 KB
+constexpr int TC_TRANSPOSE_MAX = 8;  // up to this many failing rows of a (warp, column group) are served one by one
 constexpr float TC_EPS = 1e-5f;    // slack relative to Sum x^2 + Sum y^2
 constexpr float TC_DELTA = 1e-4f;  // slack relative to the squared threshold
 
@@ -63,6 +68,7 @@ struct TcSmem {
     float cu[TC_N], cv[TC_N], cw[TC_N], cb[TC_N];  // per-column constants
     // per group of 32 columns: min Bc', [min, max] of v and w, max u (quick reject of the whole group)
     float g_bmin[TC_N / 32], g_vmin[TC_N / 32], g_vmax[TC_N / 32], g_wmin[TC_N / 32], g_wmax[TC_N / 32], g_umax[TC_N / 32];
+    int stage[TC_EPI_WARPS][32];  // one failing query row's 32 accumulators, read back one column per lane
     unsigned long long b_full, a_full[TC_STAGES], a_empty[TC_STAGES], acc_full[2], acc_empty[2];
     uint32_t tmem_base;
 };
@@ -124,8 +130,14 @@ __device__ __forceinline__ uint64_t tc_smem_desc(const void* p) {
 }
 // instruction descriptor: dense, D = s32 (bits 4-5 = 2), A = s8 (bits 7-9 = 1: the centred query codes), B = u8 (bits 10-12 = 0),
 // both K-major, N = 256, M = 128
+// HB_TC_CENTRED = 1 builds the centred operands and the per-(query, 32-column group) integer quick reject described in the
+// header comment.  MEASURED AND NOT ADOPTED (profiles/r02_k5_experiments.txt): on the C4 workload the bound rejects 75-90 %
+// of the (query, group) pairs, but a branch costs the whole warp and all 32 query rows of a warp pass together only ~6 % of
+// the time; serving the failing rows one by one (one lane per column) makes the epilogue wait-bound instead.  Both variants
+// are bit-identical to the oracle (the full brute-force suite passes with either), and both are slower than the plain
+// estimate: 11.2 ms / 12.2 ms against 10.8 ms for C4 on one GPU.
 #ifndef HB_TC_CENTRED
-#define HB_TC_CENTRED 1
+#define HB_TC_CENTRED 0
 #endif
 constexpr uint32_t TC_IDESC = (2u << 4) | (HB_TC_CENTRED ? (1u << 7) : 0u) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
 
@@ -138,8 +150,9 @@ __device__ __forceinline__ u64 mul2(u64 a, u64 b) {
 // ---- the filter kernel ---------------------------------------------------------------------------
 struct TcFilterParams {
     uint64_t row0, row_end;      // base rows of this chunk
-    const float4* bconst;        // [n_base] (u, v, w, Bc')
-    const float4* qconst;        // [nq_tiles * 128] (a0, a1, a2, a3); a0 = +inf on padding rows
+    const float4* bconst;        // [n_base] (u = db, v = P, w = ymid, Bc')
+    const float4* qconst;        // [nq_tiles * 128] (a0, a1 = -2 xmid, a2 = -2 Sum x, a3 = -2 dq); a0 = +inf on padding rows
+    const int* qshift;           // [nq_tiles * 128] 128 * Sum (cq - 128): dot'' = accumulator - qshift
     uint32_t nq, nq_tiles;
     u64* cand;                   // [nq][cap]: local base row of a survivor
     uint32_t cap;
@@ -241,6 +254,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bf_tc_filter_kernel(const __gri
             const uint32_t acc = it & 1, aph = (it >> 1) & 1;
             const uint32_t q = t * TC_M + quarter * 32 + lane;
             const float4 qc = __ldg(p.qconst + q);
+            const int qsh = HB_TC_CENTRED ? __ldg(p.qshift + q) : 0;
             const u64 a0 = pk(qc.x, qc.x), a1 = pk(qc.y, qc.y), a2 = pk(qc.z, qc.z), a3 = pk(qc.w, qc.w);
             mbar_wait(&S.acc_full[acc], aph);
             tc_fence_after();
@@ -267,6 +281,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bf_tc_filter_kernel(const __gri
                     int mx = (int)v[0];
 #pragma unroll
                     for (int j = 1; j < 32; ++j) mx = max(mx, (int)v[j]);
+                    mx -= qsh;
                     const int gi = col0 >> 5;
                     const float t1 = fminf(qc.y * S.g_vmin[gi], qc.y * S.g_vmax[gi]);
                     const float t2 = fminf(qc.z * S.g_wmin[gi], qc.z * S.g_wmax[gi]);
@@ -274,7 +289,49 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bf_tc_filter_kernel(const __gri
                     const float dterm = (-qc.w * S.g_umax[gi]) * (float)max(mx, 0);
                     // slack: far above the rounding of these few operations, far below the margins of real rejections
                     const float slack = 1e-4f * (fabsf(qc.x) + fabsf(S.g_bmin[gi]) + fabsf(t1) + fabsf(t2) + dterm);
-                    if (base_lb - dterm > slack) continue;  // NaN / -inf (non-finite parameters) fall through to the estimate
+                    const bool pass = base_lb - dterm > slack;  // false for NaN / -inf (non-finite parameters): those go on
+                    // The test is per lane (= per query row) but a branch costs the whole warp: with ~9 % of the lanes
+                    // failing, all 32 pass only ~6 % of the time.  So the few failing lanes are served one after the other
+                    // by the whole warp, one lane per COLUMN: the failing lane stages its 32 accumulators in shared memory
+                    // and broadcasts its query constants; the estimate is the same sequence of operations as below.
+                    unsigned fm = __ballot_sync(HB_FULL, !pass);
+                    if (fm == 0u) continue;
+                    if (__popc(fm) <= TC_TRANSPOSE_MAX) {
+                        int* stage = S.stage[warp - 2];
+                        const int c = col0 + lane;
+                        const float cu = S.cu[c], cv = S.cv[c], cw = S.cw[c], cb = S.cb[c];
+#pragma unroll 1
+                        while (fm) {
+                            const int f = __ffs(fm) - 1;
+                            fm &= fm - 1;
+                            if (lane == f) {
+#pragma unroll
+                                for (int j = 0; j < 32; j += 4)
+                                    *reinterpret_cast<int4*>(stage + j) = make_int4((int)v[j], (int)v[j + 1], (int)v[j + 2], (int)v[j + 3]);
+                            }
+                            __syncwarp();
+                            const float fa0 = __shfl_sync(HB_FULL, qc.x, f), fa1 = __shfl_sync(HB_FULL, qc.y, f),
+                                        fa2 = __shfl_sync(HB_FULL, qc.z, f), fa3 = __shfl_sync(HB_FULL, qc.w, f);
+                            const int fsh = __shfl_sync(HB_FULL, qsh, f);
+                            const float dotf = __int2float_rn(stage[lane] - fsh);
+                            const float base = __fadd_rn(__fmaf_rn(fa2, cw, __fmaf_rn(fa1, cv, cb)), fa0);
+                            const float ev = __fmaf_rn(__fmul_rn(fa3, cu), dotf, base);
+                            const unsigned sm = __ballot_sync(HB_FULL, ev <= 0.0f);
+                            if (sm) {
+                                const uint32_t fq = t * TC_M + quarter * 32 + f;
+                                uint32_t pos0 = 0;
+                                if (lane == 0) pos0 = atomicAdd(p.cnt + fq, (uint32_t)__popc(sm));
+                                pos0 = __shfl_sync(HB_FULL, pos0, 0);
+                                if (ev <= 0.0f) {
+                                    const uint32_t pos = pos0 + __popc(sm & ((1u << lane) - 1u));
+                                    if (pos < p.cap) p.cand[(size_t)fq * p.cap + pos] = (u64)(tile_row0 + c);
+                                    else atomicOr(p.overflow, 1u);
+                                }
+                            }
+                            __syncwarp();
+                        }
+                        continue;
+                    }
                 }
 #endif
                 float e[32];
@@ -289,8 +346,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bf_tc_filter_kernel(const __gri
                     // val = (a0 + Bc' + a1*v + a2*w) + (a3*u) * dot ; survivor iff val <= 0
                     const u64 base01 = add2(fma2(a2, pk(w4.x, w4.y), fma2(a1, pk(v4.x, v4.y), pk(b4.x, b4.y))), a0);
                     const u64 base23 = add2(fma2(a2, pk(w4.z, w4.w), fma2(a1, pk(v4.z, v4.w), pk(b4.z, b4.w))), a0);
-                    const u64 dot01 = pk(__int2float_rn((int)v[j]), __int2float_rn((int)v[j + 1]));
-                    const u64 dot23 = pk(__int2float_rn((int)v[j + 2]), __int2float_rn((int)v[j + 3]));
+                    const u64 dot01 = pk(__int2float_rn((int)v[j] - qsh), __int2float_rn((int)v[j + 1] - qsh));
+                    const u64 dot23 = pk(__int2float_rn((int)v[j + 2] - qsh), __int2float_rn((int)v[j + 3] - qsh));
                     up(fma2(mul2(a3, pk(u4.x, u4.y)), dot01, base01), e[j], e[j + 1]);
                     up(fma2(mul2(a3, pk(u4.z, u4.w)), dot23, base23), e[j + 2], e[j + 3]);
                     lo = fminf(lo, fminf(fminf(e[j], e[j + 1]), fminf(e[j + 2], e[j + 3])));
@@ -357,15 +414,19 @@ __global__ void __launch_bounds__(256) bf_tc_base_consts_kernel(const uint8_t* _
         record_stats(rec + r * L.stride, L, m, lane, wd, s1, s2, mn, dl);
         const float sb = dl * s1;
         const float bc = dl * dl * s2 + 2.0f * mn * sb + (float)L.dim * mn * mn;  // Sum y^2
+#if HB_TC_CENTRED
+        float4 k = make_float4(dl, dl * (s1 - 128.0f * (float)L.dim), mn + 128.0f * dl, bc * (1.0f - TC_EPS));  // (db, P, ymid, Bc')
+#else
         float4 k = make_float4(dl, sb + (float)L.dim * mn, mn, bc * (1.0f - TC_EPS));
+#endif
         if (!(isfinite(k.x) && isfinite(k.y) && isfinite(k.z) && isfinite(k.w))) k = make_float4(0.f, 0.f, 0.f, -INFINITY);
         if (lane == 0) out[r] = k;
     }
 }
 
-// masked, centred copy of the query records (the A operand) + (dq, xmid, dq * Sum (cq - 128), Sum x^2) per query
+// masked, centred copy of the query records (the A operand) + (dq, xmid, Sum x, Sum x^2) and the integer shift per query
 __global__ void __launch_bounds__(256) bf_tc_query_prep_kernel(const uint8_t* __restrict__ qrec, uint32_t nq, RecLayout L,
-                                                               ByteMask m, uint8_t* amask, float4* qstat) {
+                                                               ByteMask m, uint8_t* amask, float4* qstat, int* qshift) {
     const int lane = threadIdx.x & 31;
     const uint32_t warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
@@ -378,7 +439,11 @@ __global__ void __launch_bounds__(256) bf_tc_query_prep_kernel(const uint8_t* __
 #if HB_TC_CENTRED
         // A = (code - 128) as s8 on the code bytes, 0 elsewhere; x_i = (c_i - 128)*dl + xmid
         reinterpret_cast<uint32_t*>(amask + (size_t)q * TC_K)[lane] = (wd ^ 0x80808080u) & m.w[lane];
-        if (lane == 0) qstat[q] = make_float4(dl, mn + 128.0f * dl, dl * (s1 - 128.0f * (float)L.dim), qc);
+        // (dq, xmid, Sum x, Sum x^2); the integer 128 * Sum (cq - 128) goes to qshift
+        if (lane == 0) {
+            qstat[q] = make_float4(dl, mn + 128.0f * dl, sq + (float)L.dim * mn, qc);
+            qshift[q] = 128 * ((int)s1 - 128 * (int)L.dim);
+        }
 #else
         reinterpret_cast<uint32_t*>(amask + (size_t)q * TC_K)[lane] = wd;
         if (lane == 0) qstat[q] = make_float4(dl, mn, sq, qc);
@@ -400,7 +465,7 @@ __global__ void bf_tc_thresholds_kernel(const float4* __restrict__ qstat, const 
         T = t * t * (1.0f + TC_DELTA);
     }
     float a0 = s.w * (1.0f - TC_EPS) - T;
-    if (!isfinite(s.x) || !isfinite(s.y) || !isfinite(s.w)) a0 = -INFINITY;
+    if (!isfinite(s.x) || !isfinite(s.y) || !isfinite(s.z) || !isfinite(s.w)) a0 = -INFINITY;
     qconst[q] = make_float4(a0, -2.0f * s.y, -2.0f * s.z, -2.0f * s.x);
 }
 
@@ -454,12 +519,14 @@ static PFN_encodeTiled get_encode() {
     return fn;
 }
 
-// rows x 128 bytes, box = box_rows x 128 bytes, 128-byte swizzle; rows past the end read as zero
-static bool make_map(CUtensorMap* tm, const void* base, uint64_t rows, uint32_t box_rows) {
+// rows of 128 operand bytes `pitch` bytes apart (128: dim 96 / 100 records and the query copy; 144: dim 128 records, whose
+// 128 code bytes come first and whose min / delta live in the 16-byte tail), box = box_rows x 128 bytes, 128-byte swizzle;
+// rows past the end read as zero
+static bool make_map(CUtensorMap* tm, const void* base, uint64_t rows, uint32_t box_rows, uint32_t pitch = TC_K) {
     PFN_encodeTiled enc = get_encode();
     if (!enc) return false;
     cuuint64_t dims[2] = {(cuuint64_t)TC_K, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)TC_K};
+    cuuint64_t strides[1] = {(cuuint64_t)pitch};
     cuuint32_t box[2] = {(cuuint32_t)TC_K, box_rows};
     cuuint32_t estr[2] = {1, 1};
     return enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr,
@@ -468,7 +535,10 @@ static bool make_map(CUtensorMap* tm, const void* base, uint64_t rows, uint32_t 
 }
 
 bool bf_tc_supported(const RecLayout& L) {
-    return L.kind == HB_REC_QUANT && L.stride == (uint32_t)TC_K && get_encode() != nullptr;
+    // the K extent is the first 128 bytes of a record: every code byte must lie there (dim 96 / 100: 128-byte records;
+    // dim 128: 144-byte records = 128 code bytes + a 16-byte tail)
+    const bool shape = L.stride == (uint32_t)TC_K || (L.stride == 144u && L.dim == 128u);
+    return L.kind == HB_REC_QUANT && shape && get_encode() != nullptr && !getenv("HNSWB200_BF_TC_128_ONLY");
 }
 
 static ByteMask code_mask(const RecLayout& L) {
@@ -482,10 +552,10 @@ static ByteMask code_mask(const RecLayout& L) {
 }
 
 cudaError_t bf_tc_prepare(const uint8_t* base_rec, uint64_t n, const RecLayout& L, const uint8_t* qrec, uint32_t nq,
-                          float4* bconst, uint8_t* amask, float4* qstat, cudaStream_t st) {
+                          float4* bconst, uint8_t* amask, float4* qstat, int* qshift, cudaStream_t st) {
     const ByteMask m = code_mask(L);
     if (n) bf_tc_base_consts_kernel<<<(unsigned)std::min<uint64_t>((n + 7) / 8, 148 * 16), 256, 0, st>>>(base_rec, n, L, m, bconst);
-    if (nq) bf_tc_query_prep_kernel<<<(unsigned)std::min<uint32_t>((nq + 7) / 8, 148 * 16), 256, 0, st>>>(qrec, nq, L, m, amask, qstat);
+    if (nq) bf_tc_query_prep_kernel<<<(unsigned)std::min<uint32_t>((nq + 7) / 8, 148 * 16), 256, 0, st>>>(qrec, nq, L, m, amask, qstat, qshift);
     return cudaGetLastError();
 }
 
@@ -493,6 +563,7 @@ cudaError_t bf_tc_prepare(const uint8_t* base_rec, uint64_t n, const RecLayout& 
     do {                                                                           \
         if ((L).dim == 100) { using Q = RegQuery<12, 4>; __VA_ARGS__; }            \
         else if ((L).dim == 96) { using Q = RegQuery<12, 0>; __VA_ARGS__; }        \
+        else if ((L).dim == 128) { using Q = RegQuery<16, 0>; __VA_ARGS__; }       \
         else { using Q = SmemQuery; __VA_ARGS__; }                                 \
     } while (0)
 
@@ -500,15 +571,15 @@ cudaError_t bf_tc_prepare(const uint8_t* base_rec, uint64_t n, const RecLayout& 
 // survivors into `cand` (as keys).  cnt must be zero on entry; *overflow is raised if a list overflowed.
 cudaError_t bf_tc_chunk(const uint8_t* base_rec, uint64_t n_base, const RecLayout& L, uint64_t row0, uint64_t row_end,
                         uint32_t id_offset, const uint8_t* qrec, const uint8_t* amask, const float4* qstat,
-                        const float4* bconst, float4* qconst, uint32_t nq, const u64* tau, u64* cand, uint32_t cap,
-                        uint32_t* cnt, uint32_t* overflow, int num_sms, cudaStream_t st) {
+                        const float4* bconst, float4* qconst, const int* qshift, uint32_t nq, const u64* tau, u64* cand,
+                        uint32_t cap, uint32_t* cnt, uint32_t* overflow, int num_sms, cudaStream_t st) {
     if (row_end <= row0 || nq == 0) return cudaSuccess;
     const uint32_t nq_tiles = (nq + TC_M - 1) / TC_M, nq_pad = nq_tiles * TC_M;
     CUtensorMap tmA, tmB;
-    if (!make_map(&tmA, amask, nq_pad, TC_M) || !make_map(&tmB, base_rec, n_base, TC_N)) return cudaErrorNotSupported;
+    if (!make_map(&tmA, amask, nq_pad, TC_M) || !make_map(&tmB, base_rec, n_base, TC_N, L.stride)) return cudaErrorNotSupported;
     bf_tc_thresholds_kernel<<<(nq_pad + 255) / 256, 256, 0, st>>>(qstat, tau, nq, nq_pad, qconst);
     TcFilterParams p;
-    p.row0 = row0; p.row_end = row_end; p.bconst = bconst; p.qconst = qconst; p.nq = nq; p.nq_tiles = nq_tiles;
+    p.row0 = row0; p.row_end = row_end; p.bconst = bconst; p.qconst = qconst; p.qshift = qshift; p.nq = nq; p.nq_tiles = nq_tiles;
     p.cand = cand; p.cap = cap; p.cnt = cnt; p.overflow = overflow;
     const uint32_t btiles = (uint32_t)((row_end - row0 + TC_N - 1) / TC_N);
     // split the query tiles of one base tile over several CTAs when there are few base tiles

@@ -325,7 +325,7 @@ def _flat_oracle(oracle, base, dim):
                                    [(np.arange(n, dtype=np.uint32), np.zeros(n + 1, np.uint64), np.zeros(0, np.uint32))])
 
 
-@pytest.mark.parametrize("dim", [100, 96])
+@pytest.mark.parametrize("dim", [100, 96, 128])
 def test_bruteforce_tensor_core_adversarial_order(H, oracle, dim, monkeypatch):
     """The tcgen05 filter path (records of 128 bytes) with the base sorted by decreasing distance: candidate lists
     overflow, the chunk is redone by the exact kernel; and the same data through the CUDA-core path."""
