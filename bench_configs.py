@@ -205,7 +205,8 @@ def run_c3(a, E):
                          "frac": round(ab / (kern_ms / 1e3) / 1e9 / peak, 4), "traffic": None,
                          "algorithmic_bytes_per_launch": ab, "kernel_ms": round(kern_ms, 4),
                          "note": "rank 0's slice; a step = search kernel (fused peer stores) + signal + wait kernels",
-                         "per_query": {"hops": float(hops.mean()), "evals": float(evals.mean()), "nbr_ids": float(nbrs.mean())},
+                         "per_query": {"hops": float(hops.mean()), "evals": float(evals.mean()), "nbr_ids": float(nbrs.mean()),
+                                       "evals_p99": float(np.percentile(evals, 99)), "evals_max": int(evals.max())},
                          "visited_spill_queries": int(((flags & 4) != 0).sum()),
                          "visited_overflow_queries": int(((flags & 2) != 0).sum())},
             "setup": {"build_seconds": round(build_s, 2), "ground_truth_seconds": round(gt_s, 2)},

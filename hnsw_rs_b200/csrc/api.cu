@@ -942,10 +942,13 @@ static int search_dev_impl(hnswb200_ctx* c, const hnswb200_index* ix, const floa
     if (slot == 0) HB_CUDA(cudaMemsetAsync(c->d_counters, 0, hnswb200_ctx::COUNTER_RING * sizeof(uint32_t), c->stream));
     a.work_counter = c->d_counters + slot;
     a.counter_is_fresh = true;
-    if (!c->d_spill_ws) {  // 8 blocks of 4 warps per SM at most
-        const uint32_t warps = (uint32_t)c->num_sms * 32u;
-        HB_CUDA(cudaMalloc((void**)&c->d_spill_ws, (size_t)warps * hnswb200_ctx::SPILL_CAP * 4));
-        c->spill_warps = warps;
+    if (!c->d_spill_ws) {
+        const size_t words = (size_t)hnswb200_ctx::SPILL_SLICES * (1 + hnswb200_ctx::SPILL_CAP);
+        HB_CUDA(cudaMalloc((void**)&c->d_spill_ws, words * 4));
+        HB_CUDA(cudaMemsetAsync(c->d_spill_ws, 0, (size_t)hnswb200_ctx::SPILL_SLICES * 4, c->stream));  // owner words: free
+        HB_CUDA(cudaMemsetAsync(c->d_spill_ws + hnswb200_ctx::SPILL_SLICES, 0xFF, (size_t)hnswb200_ctx::SPILL_SLICES * hnswb200_ctx::SPILL_CAP * 4,
+                                c->stream));
+        c->spill_warps = hnswb200_ctx::SPILL_SLICES;
     }
     a.spill_ws = c->d_spill_ws;
     a.spill_cap = hnswb200_ctx::SPILL_CAP;

@@ -66,8 +66,11 @@ struct hnswb200_ctx {
     void* d_bf_ws = nullptr;        // grow-only scratch of the brute-force entry points (cudaMalloc per call costs more than the kernels)
     size_t bf_ws_bytes = 0;
     int bf_ws_reserve(size_t bytes);
-    uint32_t* d_spill_ws = nullptr;  // visited-set spill continuation of the search kernel: SPILL_CAP ids per resident warp
-    static constexpr uint32_t SPILL_CAP = 1024;
+    // global continuation of the search kernel's visited spill set (csrc/search_fast.cuh, SpillPool): SPILL_SLICES owner
+    // words (0 = free) followed by SPILL_SLICES hash sets of SPILL_CAP ids, every entry free (0xFF) while a slice is not lent
+    uint32_t* d_spill_ws = nullptr;
+    static constexpr uint32_t SPILL_CAP = 4096;  // power of two
+    static constexpr uint32_t SPILL_SLICES = 1024;
     uint32_t spill_warps = 0;
     std::vector<uint32_t> h_flags;
     uint32_t* h_status = nullptr;   // pinned + mapped host word the search kernel raises on a NaN query

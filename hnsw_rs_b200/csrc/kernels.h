@@ -45,7 +45,8 @@ struct SearchLaunch {
     uint32_t* work_counter;  // device u32, zero on entry
     bool counter_is_fresh = false;  // true: the caller guarantees *work_counter == 0 (no memset is enqueued)
     bool overlap_previous = false;  // launch as programmatic dependent of the previous kernel in the stream
-    // optional global continuation of the visited set's exact spill list (search_fast.cuh): spill_cap ids per warp
+    // optional global continuation of the visited set's exact spill set (search_fast.cuh, SpillPool): spill_warps owner
+    // words followed by spill_warps slices of spill_cap ids (a power of two)
     uint32_t* spill_ws = nullptr;
     uint32_t spill_cap = 0, spill_warps = 0;
 };

@@ -64,8 +64,11 @@ __global__ void __launch_bounds__(SEARCH_WPB * 32, MINB) search_kernel_fast(Sear
         SearchCounters cnt{0u, 0u, 0u, 0u};
         RegList<KPL> L;
         __syncwarp();  // every lane has copied its part of qd before the scratch area is reused
-        search_query_fast<Q, KPL, STATS>(q, p.rec, p.L.stride, p.g, p.n_layers, p.ep, L, vis, wsm, spill_ws, spill_cap,
-                                         (int)p.ef, lane, cnt);
+        SpillPool pool;
+        pool.base = spill_ws;
+        pool.npool = spill_cap >> 16;      // packed by the launcher: slices << 16 | log2(ids per slice)
+        pool.cap = 1u << (spill_cap & 31u);
+        search_query_fast<Q, KPL, STATS>(q, p.rec, p.L.stride, p.g, p.n_layers, p.ep, L, vis, wsm, pool, (int)p.ef, lane, cnt);
         // get_top_selected(n)   (results.rs:59-61): position lane*KPL + s
         uint32_t mine = 0;
         uint32_t* sid = reinterpret_cast<uint32_t*>(scratch);  // staged row for the peer stores
@@ -163,7 +166,10 @@ static cudaError_t launch_fast_s(const SearchParams& p, int num_sms, cudaStream_
     }
     const uint64_t cap = (uint64_t)num_sms * occ;
     int grid = (int)(want < cap ? want : cap);
-    if (spill_ws && (uint64_t)grid * SEARCH_WPB > spill_warps) spill_cap = 0;  // workspace too small for this grid: no global continuation
+    // spill pool geometry packed into one kernel argument: slices << 16 | log2(ids per slice)
+    uint32_t lg = 5;
+    while ((1u << (lg + 1)) <= spill_cap) ++lg;
+    const uint32_t pool_arg = spill_ws && spill_warps && spill_cap >= 32 ? (spill_warps << 16) | lg : 0u;
     char name[160];
     snprintf(name, sizeof name, "hb::search_kernel_fast<FastQuery<%s>,KPL=%d,STATS=%d,blocks/SM=%d,VisB4 %u buckets>", qname, KPL,
              (int)STATS, occ_cache, nb);
@@ -179,14 +185,15 @@ static cudaError_t launch_fast_s(const SearchParams& p, int num_sms, cudaStream_
     cfg.attrs = at;
     cfg.numAttrs = overlap_previous ? 1 : 0;
     const uint32_t vmul = 0x9E3779B1u << (32u - bbits), vrsh = 38u - bbits;
-    return cudaLaunchKernelEx(&cfg, kern, p, nb, vmul, vrsh, spill_cap ? spill_ws : (uint32_t*)nullptr, spill_cap);
+    return cudaLaunchKernelEx(&cfg, kern, p, nb, vmul, vrsh, pool_arg ? spill_ws : (uint32_t*)nullptr, pool_arg);
 }
 
 #ifndef HB_FAST_MINB2
 #define HB_FAST_MINB2 8  // resident blocks per SM of the ef <= 64 variant (64 registers, 576 visited buckets)
 #endif
 #ifndef HB_FAST_MINB4
-#define HB_FAST_MINB4 7  // ef <= 128 (70 registers, 704 visited buckets)
+#define HB_FAST_MINB4 5  // ef <= 128: the visited set of such a query holds 1,000-3,000 ids, so table size counts for more than a sixth block
+                         // (C3, 1M x 128, ef = 100: 4.58 M q/s with 5 blocks x 1024 buckets, 4.15 M with 6 x 896, 3.06 M with 7 x 704)
 #endif
 
 template <class Q>

@@ -35,8 +35,10 @@
 
 namespace hb {
 
-constexpr int FAST_SPILL = 16;        // words of the shared-memory spill area: 14 ids + the two list lengths
-constexpr int FAST_SPILL_IDS = FAST_SPILL - 2;
+constexpr int FAST_SPILL = 16;        // words of the shared-memory spill area: 12 ids, their number, the number of ids in the
+                                      // global set, the global slice this query holds (+1; 0 = none), one spare
+constexpr int FAST_SPILL_IDS = 12;
+constexpr int FAST_SPILL_N1 = 12, FAST_SPILL_N2 = 13, FAST_SPILL_SLICE = 14;
 constexpr int FAST_ACC_STRIDE = 12;   // floats per candidate in the accumulator buffer: acc[0..8), remainder squares [8..12)
 constexpr uint32_t FAST_SCRATCH_BYTES = 32 * FAST_ACC_STRIDE * 4;  // 1536: accumulators | admitted keys + merge buffer | query
 
@@ -108,7 +110,7 @@ struct VisB4 {
         const uint32_t n16 = nb / 2;  // 16-byte chunks
         for (uint32_t i = lane; i < n16; i += 32)
             asm volatile("st.shared.v4.u32 [%0], {%1,%1,%1,%1};" ::"r"(sbase + i * 16u), "r"(0xFFFFFFFFu) : "memory");
-        if (lane == 0) { spill[FAST_SPILL_IDS] = 0u; spill[FAST_SPILL_IDS + 1] = 0u; }
+        if (lane == 0) { spill[FAST_SPILL_N1] = 0u; spill[FAST_SPILL_N2] = 0u; }
         __syncwarp();
     }
     // results.insert_visited for all 32 lanes (want: this lane holds an id).  Returns "id was not yet visited" per
@@ -130,41 +132,100 @@ struct VisB4 {
     }
 };
 
-// Out-of-line: the lanes in `om` hold ids that found 8 full buckets in a row.  The exact spill list decides whether
-// such an id was seen before (shared memory first, then this warp's slice of a global workspace); when both are
-// full, list membership keeps the answers exact and only the evaluation counter may over-count (*flags bit 1).
+// Global continuation of the spill set: a small pool of slices (hash sets of `cap` 32-bit ids, 0xFFFFFFFF = free) that a
+// query borrows when its 12 shared-memory entries are used up and returns, wiped, when it is done.  pool[0..npool) are
+// the owner words (0 = free), the slices follow.  Overlapping launches of one context (PDL) share the pool safely:
+// a slice has one owner at a time.
+struct SpillPool {
+    uint32_t* base;
+    uint32_t npool, cap;  // cap: a power of two >= 32
+    __device__ __forceinline__ uint32_t* slice(uint32_t i) const { return base + npool + (size_t)i * cap; }
+};
+
+// Out-of-line: the lanes in `om` hold ids that found 8 full buckets in a row.  The exact spill set decides whether such an
+// id was seen before: up to 12 ids in shared memory; once those are used up, a borrowed global slice used as an open-
+// addressing hash set in which ALL the lanes concerned probe at once (compare-and-swap on 32-bit entries; the ids of a batch
+// are distinct).  When no slice can be had or a probe sequence runs too long, list membership keeps the answers exact and
+// only the evaluation counter may over-count (flag bit 1).
 // Returns bit0: this lane's "id is new"; bits 1-2: the flag bits to raise.
 template <int KPL>
-__device__ __noinline__ uint32_t vis_spill(uint32_t* spill, uint32_t* gspill, uint32_t gcap, unsigned om, uint32_t nb,
-                                           bool isnew, const RegList<KPL> L, int lane) {
+__device__ __noinline__ uint32_t vis_spill(uint32_t* spill, SpillPool pool, unsigned om, uint32_t nb, bool isnew,
+                                           const RegList<KPL> L, int lane) {
     uint32_t fl = 4u;
-    while (om) {
-        const int src = __ffs(om) - 1;
-        om &= om - 1;
-        const uint32_t id = __shfl_sync(HB_FULL, nb, src);
-        uint32_t n1 = spill[FAST_SPILL_IDS], n2 = spill[FAST_SPILL_IDS + 1];
-        bool hit = (uint32_t)lane < n1 && spill[lane] == id;
-        for (uint32_t base = 0; base < n2; base += 32)
-            hit = hit || (base + lane < n2 && *reinterpret_cast<volatile uint32_t*>(gspill + base + lane) == id);
-        bool fresh;
-        if (__any_sync(HB_FULL, hit)) fresh = false;
-        else if (n1 < (uint32_t)FAST_SPILL_IDS) {
-            if (lane == 0) { spill[n1] = id; spill[FAST_SPILL_IDS] = n1 + 1u; }
-            fresh = true;
-        } else if (n2 < gcap) {
-            if (lane == 0) {
-                *reinterpret_cast<volatile uint32_t*>(gspill + n2) = id;
-                spill[FAST_SPILL_IDS + 1] = n2 + 1u;
-            }
-            fresh = true;
-        } else {
-            fl |= 2u;
-            fresh = !L.holds_id(id);
-        }
+    const bool mine = (om >> lane) & 1u;
+    const uint32_t n1 = spill[FAST_SPILL_N1];
+    bool found = false;
+    for (uint32_t i = 0; i < n1; ++i) found = found || spill[i] == nb;  // broadcast reads
+    bool pending = mine && !found;
+    unsigned pm = __ballot_sync(HB_FULL, pending);
+    if (pm == 0u) return fl | (isnew ? 1u : 0u);
+    uint32_t sl = spill[FAST_SPILL_SLICE];  // slice index + 1
+    if (sl == 0u && n1 + (uint32_t)__popc(pm) <= (uint32_t)FAST_SPILL_IDS) {  // room in the shared-memory list
+        if (pending) spill[n1 + __popc(pm & ((1u << lane) - 1u))] = nb;
+        if (lane == 0) spill[FAST_SPILL_N1] = n1 + (uint32_t)__popc(pm);
         __syncwarp();
-        if (lane == src) isnew = fresh;
+        return fl | ((isnew || pending) ? 1u : 0u);
     }
-    return fl | (isnew ? 1u : 0u);
+    if (sl == 0u && pool.base) {  // borrow a slice
+        if (lane == 0) {
+            const uint32_t start = (blockIdx.x * SEARCH_WPB + (threadIdx.x >> 5)) % pool.npool;
+            for (uint32_t k = 0; k < pool.npool && sl == 0u; ++k) {
+                const uint32_t i = start + k < pool.npool ? start + k : start + k - pool.npool;
+                if (atomicCAS(pool.base + i, 0u, 1u) == 0u) sl = i + 1u;
+            }
+            __threadfence();  // the previous owner's wipe is visible before this query reads the slice
+            spill[FAST_SPILL_SLICE] = sl;
+        }
+        sl = __shfl_sync(HB_FULL, sl, 0);
+    }
+    bool fresh = false, over = pending && sl == 0u;
+    if (sl != 0u) {
+        uint32_t* g = pool.slice(sl - 1u);
+        const uint32_t mask = pool.cap - 1u;
+        uint32_t h = ((nb * 0x9E3779B1u) >> 7) & mask;
+        int probes = 0;
+        while (__any_sync(HB_FULL, pending)) {
+            uint32_t old = nb;
+            if (pending) old = atomicCAS(g + h, 0xFFFFFFFFu, nb);
+            const bool won = pending && old == 0xFFFFFFFFu;
+            const bool step = pending && !won && old != nb;
+            fresh = fresh || won;
+            h = step ? ((h + 1u) & mask) : h;
+            probes += step ? 1 : 0;
+            over = over || (step && probes >= 96);  // the set is too full for this id
+            pending = step && !over;
+        }
+        const unsigned wm = __ballot_sync(HB_FULL, fresh);
+        if (lane == 0 && wm) spill[FAST_SPILL_N2] = spill[FAST_SPILL_N2] + (uint32_t)__popc(wm);
+    }
+    unsigned ovm = __ballot_sync(HB_FULL, over);
+    if (ovm) {
+        fl |= 2u;
+        while (ovm) {
+            const int src = __ffs(ovm) - 1;
+            ovm &= ovm - 1;
+            const bool in_list = L.holds_id(__shfl_sync(HB_FULL, nb, src));
+            if (lane == src) fresh = !in_list;
+        }
+    }
+    __syncwarp();
+    return fl | ((isnew || fresh) ? 1u : 0u);
+}
+
+// A query that borrowed a global slice wipes it and gives it back (at the end of every layer search that used it).
+__device__ __noinline__ void spill_release(uint32_t* spill, SpillPool pool, int lane) {
+    const uint32_t sl = spill[FAST_SPILL_SLICE];
+    if (sl == 0u) return;
+    uint32_t* g = pool.slice(sl - 1u);
+    for (uint32_t i = lane * 4u; i < pool.cap; i += 128u)
+        *reinterpret_cast<uint4*>(g + i) = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+    __syncwarp();
+    if (lane == 0) {
+        __threadfence();
+        atomicExch(pool.base + (sl - 1u), 0u);
+        spill[FAST_SPILL_SLICE] = 0u;
+    }
+    __syncwarp();
 }
 
 // Query of a compile-time dimension (8*NCH + REM, REM <= 4) in registers; evaluates one record per group of 4 lanes
@@ -190,12 +251,25 @@ struct FastQuery {
     static constexpr int TAIL = RQ::TAIL;
     using Rec = typename RQ::Rec;
     static constexpr int kRem = REM;
+    static constexpr uint32_t kStride = 64u * W + 16u * TAIL;  // bytes per record (csrc/layout.h)
+    // request the lines of one record (L2)
+    __device__ __forceinline__ static void prefetch(const uint8_t* rp) {
+        prefetch_l2(rp);
+        if (kStride > 128u || (kStride % 128u) != 0u) prefetch_l2(rp + kStride - 1);  // a record that can straddle lines
+    }
     // remainder bytes: tail form -> bytes 8..11 of the tail word; compact form -> lane 0's slice positions 2*NCH + r
     static constexpr int RP0 = TAIL ? 8 : 2 * NCH;             // slice position (or tail byte) of remainder element 0
     static constexpr bool STRADDLE = REM > 0 && (RP0 % 4) + REM > 4;  // the REM bytes span two 32-bit words
 #if HB_FAST_QSMEM
-    const u64* qs;    // this lane's column of the [chunk][lane of group] table in shared memory
-    __device__ __forceinline__ u64 qk(int k) const { return qs[4 * k]; }
+    static constexpr int QROW = (NCH + 1) / 2 * 2;  // chunks per lane of a group, padded to whole 16-byte loads
+    const u64* qs;    // this lane's row of the [lane of group][chunk] table in shared memory (16-byte aligned)
+    __device__ __forceinline__ u64 qk(int k) const { return qs[k]; }
+    // two chunks per 16-byte load
+    __device__ __forceinline__ void qk2(int k, u64& a, u64& b) const {
+        const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(qs + k);
+        a = v.x;
+        b = v.y;
+    }
 #else
     u64 q[NCH ? NCH : 1];
     __device__ __forceinline__ u64 qk(int k) const { return q[k]; }
@@ -207,12 +281,12 @@ struct FastQuery {
     // for the whole query (only used when the query lives in shared memory)
     __device__ __forceinline__ void init(const RecLayout&, const float* qd, int gl, u64* qtab, int lane) {
 #if HB_FAST_QSMEM
-        for (int i = lane; i < 4 * NCH; i += 32) {  // entry (k, l) = values 8k+2l, 8k+2l+1
+        for (int i = lane; i < 4 * NCH; i += 32) {  // entry (l, k) = values 8k+2l, 8k+2l+1
             const int k = i >> 2, l = i & 3;
             float2 v = *reinterpret_cast<const float2*>(qd + 8 * k + 2 * l);
-            qtab[i] = pk(v.x, v.y);
+            qtab[l * QROW + k] = pk(v.x, v.y);
         }
-        qs = qtab + gl;
+        qs = qtab + gl * QROW;
 #else
 #pragma unroll
         for (int k = 0; k < NCH; ++k) {
@@ -270,11 +344,28 @@ struct FastQuery {
             const u64 dl2 = pk(dl, dl);
             const float nmd = __fmul_rn(-8388608.0f, dl);
             const u64 nmd2 = pk(nmd, nmd);
+#if HB_FAST_QSMEM
+#pragma unroll
+            for (int k = 0; k + 1 < NCH; k += 2) {
+                u64 qa, qb;
+                qk2(k, qa, qb);
+                const u64 ma = pk(RQ::slice_magic(w, 2 * k), RQ::slice_magic(w, 2 * k + 1));
+                acc = add2(acc, chunk_sq(ma, dl2, nmd2, mn2, qa, nz));
+                const u64 mb = pk(RQ::slice_magic(w, 2 * k + 2), RQ::slice_magic(w, 2 * k + 3));
+                acc = add2(acc, chunk_sq(mb, dl2, nmd2, mn2, qb, nz));
+            }
+            if (NCH & 1) {
+                constexpr int k = NCH - 1;
+                const u64 m2 = pk(RQ::slice_magic(w, 2 * k), RQ::slice_magic(w, 2 * k + 1));
+                acc = add2(acc, chunk_sq(m2, dl2, nmd2, mn2, qk(k), nz));
+            }
+#else
 #pragma unroll
             for (int k = 0; k < NCH; ++k) {
                 const u64 m2 = pk(RQ::slice_magic(w, 2 * k), RQ::slice_magic(w, 2 * k + 1));
                 acc = add2(acc, chunk_sq(m2, dl2, nmd2, mn2, qk(k), nz));
             }
+#endif
             if (REM > 0) {
                 // one remainder element per lane; the second half of the packed pair is a dummy (code 0 against 0)
                 const float fm = __uint_as_float(__byte_perm(rw, 0x4B000000u, remsel));
@@ -376,12 +467,12 @@ __device__ __forceinline__ void merge_ranked(RegList<KPL>& L, u64 key, bool want
 }
 
 // One whole query.  On exit L holds the <= ef nearest evaluated nodes of layer 0, sorted.
-// gspill / gcap: this warp's slice of the global continuation of the spill list (may be null / 0).
+// pool: the global continuation of the spill set (base may be null).
 template <class Q, int KPL, bool STATS>
 __device__ __forceinline__ void search_query_fast(const Q& query, const uint8_t* __restrict__ rec, uint32_t rec_stride,
                                                   const GraphView& g, uint32_t n_layers, uint32_t ep, RegList<KPL>& L,
-                                                  const VisB4& vis, unsigned char* wsm, uint32_t* gspill_ws, uint32_t gcap,
-                                                  int ef, int lane, SearchCounters& cnt) {
+                                                  const VisB4& vis, unsigned char* wsm, const SpillPool pool, int ef, int lane,
+                                                  SearchCounters& cnt) {
     uint32_t* newbuf = reinterpret_cast<uint32_t*>(wsm);
     float* scratch = reinterpret_cast<float*>(wsm + FAST_OFF_SCRATCH);
     // key at position ef_l - 1 of the list (the sentinel, i.e. the maximum, while |selected| < ef_l): kept in shared
@@ -398,7 +489,10 @@ __device__ __forceinline__ void search_query_fast(const Q& query, const uint8_t*
     uint32_t layer = n_layers - 1;
     int len = 0;  // |selected|
     L.reset();
-    if (lane == 0) *worst_p = RSENT;
+    if (lane == 0) {
+        *worst_p = RSENT;
+        vis.spill[FAST_SPILL_SLICE] = 0u;
+    }
     vis.clear(lane);
     // boot batch: the entry point (selected <- {Dist(ep, d)}, template.rs:316-319)
     uint32_t nb = lane == 0 ? ep : EMPTY_ID;
@@ -415,14 +509,13 @@ __device__ __forceinline__ void search_query_fast(const Q& query, const uint8_t*
         const bool valid = !(nb & CHAIN_BIT);  // EMPTY_ID and chain markers carry bit 31
 #if HB_FAST_PREFETCH_ALL
         // request the record of every neighbour before the visited test (unless that happened a hop ago: speculation hit)
-        if (fresh_row && valid) prefetch_record(rec + (size_t)nb * rec_stride, rec_stride);
+        if (fresh_row && valid) Q::prefetch(rec + (size_t)nb * Q::kStride);
 #endif
         fresh_row = false;
         bool ovf;
         bool isnew = vis.insert_warp(nb, valid, ovf);
         if (__any_sync(HB_FULL, ovf)) {  // rare: 8 full buckets in a row
-            uint32_t* gsp = gspill_ws ? gspill_ws + ((size_t)blockIdx.x * SEARCH_WPB + (threadIdx.x >> 5)) * gcap : nullptr;
-            const uint32_t r = vis_spill<KPL>(vis.spill, gsp, gsp ? gcap : 0u, __ballot_sync(HB_FULL, ovf), nb, isnew, L, lane);
+            const uint32_t r = vis_spill<KPL>(vis.spill, pool, __ballot_sync(HB_FULL, ovf), nb, isnew, L, lane);
             isnew = (r & 1u) != 0u;
             if (STATS) cnt.overflow |= r & 6u;
         }
@@ -433,7 +526,7 @@ __device__ __forceinline__ void search_query_fast(const Q& query, const uint8_t*
         if (spec_pending) {
             // the row of the probable next expansion has arrived by now (it was requested at the pop): request the records
             // of its neighbours a whole hop before they are evaluated
-            if (!(spec_nb & CHAIN_BIT)) prefetch_record(rec + (size_t)spec_nb * rec_stride, rec_stride);
+            if (!(spec_nb & CHAIN_BIT)) Q::prefetch(rec + (size_t)spec_nb * Q::kStride);
             spec_pending = false;
         }
 #endif
@@ -443,7 +536,7 @@ __device__ __forceinline__ void search_query_fast(const Q& query, const uint8_t*
                 const int my = __popc(nm & lt);
                 newbuf[my] = nb;
 #if !HB_FAST_PREFETCH_ALL
-                prefetch_record(rec + (size_t)nb * rec_stride, rec_stride);
+                Q::prefetch(rec + (size_t)nb * Q::kStride);
 #endif
             }
             __syncwarp();
@@ -452,7 +545,7 @@ __device__ __forceinline__ void search_query_fast(const Q& query, const uint8_t*
                 // two record buffers: the loads of round r+1 are in flight while round r is evaluated
                 auto rec_of = [&](int r0) {
                     const int idx = r0 + grp;
-                    return Q::load(rec + (size_t)newbuf[idx < ncnt ? idx : 0] * rec_stride, gl);
+                    return Q::load(rec + (size_t)newbuf[idx < ncnt ? idx : 0] * Q::kStride, gl);
                 };
                 auto eval = [&](const typename Q::Rec& R, int r0) {
                     const int idx = r0 + grp;
@@ -483,7 +576,7 @@ __device__ __forceinline__ void search_query_fast(const Q& query, const uint8_t*
                 // index.get_point(node).dist2other(point)  (searcher.rs:66-69), the sum left to the lanes below
                 u64 acc;
                 float rsq;
-                query.partial(Q::load(rec + (size_t)cand * rec_stride, gl), gl, gbase, acc, rsq);
+                query.partial(Q::load(rec + (size_t)cand * Q::kStride, gl), gl, gbase, acc, rsq);
                 *reinterpret_cast<u64*>(accbuf + idx * FAST_ACC_STRIDE + 2 * gl) = acc;
                 if (Q::kRem > 0) accbuf[idx * FAST_ACC_STRIDE + 8 + gl] = rsq;
             }
@@ -547,13 +640,17 @@ __device__ __forceinline__ void search_query_fast(const Q& query, const uint8_t*
             if (!L.pop(cid, lane)) {
                 // this layer is finished: selected survives as the entry set of the next one
                 L.clear_flags();
-                if (layer == 0) break;
+                if (layer == 0) {
+                    if (vis.spill[FAST_SPILL_SLICE] != 0u) spill_release(vis.spill, pool, lane);
+                    break;
+                }
                 --layer;
                 {
                     const int efn = layer ? 1 : ef;
                     const u64 w = len == efn ? L.get(efn - 1) : RSENT;
                     if (lane == 0) *worst_p = w;
                 }
+                if (vis.spill[FAST_SPILL_SLICE] != 0u) spill_release(vis.spill, pool, lane);
                 vis.clear(lane);
                 // seed batch: visited <- ids(selected); the upper layers ran with ef = 1, so the entry set is the
                 // single key at position 0
