@@ -1189,7 +1189,7 @@ int hnswb200_bruteforce_topk_dev(hnswb200_ctx* c, const hnswb200_points* base, c
     if (c->use()) return HNSWB200_ECUDA;
     const RecLayout& L = base->L;
     const uint32_t cap = 2048;
-    const uint64_t N = base->n, MAXCH = 1ull << 18;
+    const uint64_t N = base->n;
     // Tensor-core filter (bf_tc.cu) for every chunk after the first: the first (exact) chunk establishes
     // the thresholds.  HNSWB200_BF_NO_TC forces the CUDA-core path (test knob).
     const bool use_tc = bf_tc_supported(L) && N > 2 * cap && !getenv("HNSWB200_BF_NO_TC");
@@ -1239,44 +1239,53 @@ int hnswb200_bruteforce_topk_dev(hnswb200_ctx* c, const hnswb200_points* base, c
         HB_CUDA(cudaMemsetAsync(W + o_qshift, 0, nq_pad * 4, c->stream));
         HB_CUDA(bf_tc_prepare(base->d_rec, N, L, qrec.p, (uint32_t)nq, bconst.p, amask.p, qstat.p, (int*)(W + o_qshift), c->stream));
     }
-    uint64_t done = 0;
-    while (done < N) {
-        // first chunk: enough rows for a useful k-th distance, few enough for a cheap merge
+    const bool prof = getenv("HNSWB200_BF_PROFILE") != nullptr;
+    bool tc_done = false;
+    if (use_tc) {
+        // Optimistic pass, no host synchronisation between the chunks: the first rows are ranked exactly (every pair of
+        // them is a survivor), then chunks that multiply the rows seen by `grow`.  With tau = the k-th best of n rows in
+        // random order, a chunk of (grow-1)*n rows leaves about k*ln(grow) survivors per query, far below `cap`.  The
+        // overflow flag is read once at the end; an order that overflows a list (sorted by decreasing distance, say)
+        // sends the whole call through the exact path below.
         uint64_t first = 256;
         while (first < 4ull * k && first < cap) first <<= 1;
-        uint64_t ch = done == 0 ? std::min<uint64_t>(use_tc ? first : cap, N) : std::min<uint64_t>(std::min<uint64_t>(done, MAXCH), N - done);
-        if (use_tc && done > 0)
+        first = std::min<uint64_t>(first, N);
+        const uint64_t grow = (4ull * k <= cap) ? 4 : 2, TC_MAXCH = 1ull << 20;
+        HB_CUDA(bf_tc_first(base->d_rec, L, (uint32_t)first, id_offset, qrec.p, (uint32_t)nq,
+                            reinterpret_cast<unsigned long long*>(buf.p), cap, cnt.p, c->stream));
+        HB_CUDA(launch_bf_merge(topk.p, k, tau.p, buf.p, cap, cnt.p, (uint32_t)nq, c->stream));
+        uint64_t done = first;
+        while (done < N) {
+            const uint64_t ch = std::min<uint64_t>(std::min<uint64_t>(done * (grow - 1), TC_MAXCH), N - done);
             HB_CUDA(bf_tc_chunk(base->d_rec, N, L, done, done + ch, id_offset, qrec.p, amask.p, qstat.p, bconst.p, qconst.p,
                                 (const int*)(W + o_qshift), (uint32_t)nq, reinterpret_cast<const unsigned long long*>(tau.p),
                                 reinterpret_cast<unsigned long long*>(buf.p), cap, cnt.p, ovf_flag, c->num_sms, c->stream));
-        else
-            HB_CUDA(launch_bf_chunk(base->d_rec, L, done, done + ch, id_offset, qrec.p, (uint32_t)nq, tau.p, buf.p,
-                                    cap, cnt.p, ovf_flag, c->stream));
+            HB_CUDA(launch_bf_merge(topk.p, k, tau.p, buf.p, cap, cnt.p, (uint32_t)nq, c->stream));
+            if (prof) fprintf(stderr, "[hnswb200 bruteforce] rows [%llu, %llu) tensor-core filter (enqueued)\n",
+                              (unsigned long long)done, (unsigned long long)(done + ch));
+            done += ch;
+        }
         uint32_t ovf = 0;
         HB_CUDA(cudaMemcpyAsync(&ovf, ovf_flag, 4, cudaMemcpyDeviceToHost, c->stream));
         HB_CUDA(cudaStreamSynchronize(c->stream));
-        if (getenv("HNSWB200_BF_PROFILE")) {
-            static double t_prev = 0;
-            timespec ts;
-            clock_gettime(CLOCK_MONOTONIC, &ts);
-            double t_now = ts.tv_sec + ts.tv_nsec * 1e-9;
-            fprintf(stderr, "[hnswb200 bruteforce] rows [%llu, %llu) %s overflow=%u  +%.2f ms\n", (unsigned long long)done,
-                    (unsigned long long)(done + ch), (use_tc && done > 0) ? "tensor-core filter" : "exact", ovf,
-                    (t_now - t_prev) * 1e3);
-            t_prev = t_now;
-        }
-        if (ovf) {
+        if (prof) fprintf(stderr, "[hnswb200 bruteforce] optimistic pass done, overflow=%u\n", ovf);
+        if (!ovf) tc_done = true;
+        else {  // start over on the exact path
             HB_CUDA(cudaMemsetAsync(ovf_flag, 0, 4, c->stream));
+            HB_CUDA(cudaMemsetAsync(topk.p, 0xFF, nq * k * 8, c->stream));
+            HB_CUDA(cudaMemsetAsync(tau.p, 0xFF, nq * 8, c->stream));
             HB_CUDA(cudaMemsetAsync(cnt.p, 0, nq * 4, c->stream));
-            for (uint64_t s = done; s < done + ch; s += cap) {
-                uint64_t e = std::min<uint64_t>(s + cap, done + ch);
-                HB_CUDA(launch_bf_chunk(base->d_rec, L, s, e, id_offset, qrec.p, (uint32_t)nq, tau.p, buf.p, cap,
-                                        cnt.p, ovf_flag, c->stream));
-                HB_CUDA(launch_bf_merge(topk.p, k, tau.p, buf.p, cap, cnt.p, (uint32_t)nq, c->stream));
-            }
-        } else {
-            HB_CUDA(launch_bf_merge(topk.p, k, tau.p, buf.p, cap, cnt.p, (uint32_t)nq, c->stream));
         }
+    }
+    // Exact CUDA-core path (record shapes without a tensor-core path, small bases, adversarial orders): chunks of `cap`
+    // rows cannot overflow a list of `cap` entries.
+    for (uint64_t done = 0; !tc_done && done < N;) {
+        const uint64_t ch = std::min<uint64_t>(cap, N - done);
+        HB_CUDA(launch_bf_chunk(base->d_rec, L, done, done + ch, id_offset, qrec.p, (uint32_t)nq, tau.p, buf.p, cap, cnt.p,
+                                ovf_flag, c->stream));
+        HB_CUDA(launch_bf_merge(topk.p, k, tau.p, buf.p, cap, cnt.p, (uint32_t)nq, c->stream));
+        if (prof) fprintf(stderr, "[hnswb200 bruteforce] rows [%llu, %llu) exact (enqueued)\n", (unsigned long long)done,
+                          (unsigned long long)(done + ch));
         done += ch;
     }
     HB_CUDA(launch_keys_to_out(topk.p, k, (uint32_t)nq, d_out_ids, d_out_dists, c->stream));

@@ -500,6 +500,15 @@ __global__ void __launch_bounds__(128) bf_rerank_kernel(const uint8_t* __restric
     }
 }
 
+// the first rows of the base: every (query, row) pair is a "survivor"
+__global__ void __launch_bounds__(256) bf_fill_first_kernel(u64* cand, uint32_t cap, uint32_t* cnt, uint32_t nq, uint32_t first) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (uint64_t)nq * first) return;
+    const uint32_t q = (uint32_t)(i / first), r = (uint32_t)(i % first);
+    cand[(size_t)q * cap + r] = r;
+    if (r == 0) cnt[q] = first;
+}
+
 // ---- host side -----------------------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -559,6 +568,8 @@ cudaError_t bf_tc_prepare(const uint8_t* base_rec, uint64_t n, const RecLayout& 
     return cudaGetLastError();
 }
 
+
+
 #define HB_DISPATCH_DIM_T(L, ...)                                                  \
     do {                                                                           \
         if ((L).dim == 100) { using Q = RegQuery<12, 4>; __VA_ARGS__; }            \
@@ -566,6 +577,22 @@ cudaError_t bf_tc_prepare(const uint8_t* base_rec, uint64_t n, const RecLayout& 
         else if ((L).dim == 128) { using Q = RegQuery<16, 0>; __VA_ARGS__; }       \
         else { using Q = SmemQuery; __VA_ARGS__; }                                 \
     } while (0)
+
+// Rows [0, first) of the base ranked exactly against every query (no threshold exists yet): `cand` receives the keys.
+cudaError_t bf_tc_first(const uint8_t* base_rec, const RecLayout& L, uint32_t first, uint32_t id_offset, const uint8_t* qrec,
+                        uint32_t nq, u64* cand, uint32_t cap, uint32_t* cnt, cudaStream_t st) {
+    if (first == 0 || nq == 0) return cudaSuccess;
+    if (first > cap) return cudaErrorInvalidValue;
+    const uint64_t tot = (uint64_t)nq * first;
+    bf_fill_first_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(cand, cap, cnt, nq, first);
+    const uint32_t qd_cap = (L.dim + 7) / 8 * 8 + 8;
+    const size_t rsm = (size_t)4 * qd_cap * 4;
+    HB_DISPATCH_DIM_T(L, {
+        cudaFuncSetAttribute(bf_rerank_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm);
+        bf_rerank_kernel<Q><<<std::min<uint32_t>((nq + 3) / 4, 148 * 8), 128, rsm, st>>>(base_rec, L, id_offset, qrec, nq, cand, cap, cnt);
+    });
+    return cudaGetLastError();
+}
 
 // One chunk [row0, row_end) of the base: thresholds from tau, tensor-core filter, exact re-rank of the
 // survivors into `cand` (as keys).  cnt must be zero on entry; *overflow is raised if a list overflowed.

@@ -98,6 +98,8 @@ cudaError_t launch_keys_to_out(const uint64_t* topk, uint32_t k, uint32_t nq, ui
 bool bf_tc_supported(const RecLayout& L);
 cudaError_t bf_tc_prepare(const uint8_t* base_rec, uint64_t n, const RecLayout& L, const uint8_t* qrec, uint32_t nq,
                           float4* bconst, uint8_t* amask, float4* qstat, int* qshift, cudaStream_t st);
+cudaError_t bf_tc_first(const uint8_t* base_rec, const RecLayout& L, uint32_t first, uint32_t id_offset, const uint8_t* qrec,
+                        uint32_t nq, unsigned long long* cand, uint32_t cap, uint32_t* cnt, cudaStream_t st);
 cudaError_t bf_tc_chunk(const uint8_t* base_rec, uint64_t n_base, const RecLayout& L, uint64_t row0, uint64_t row_end,
                         uint32_t id_offset, const uint8_t* qrec, const uint8_t* amask, const float4* qstat,
                         const float4* bconst, float4* qconst, const int* qshift, uint32_t nq, const unsigned long long* tau,
