@@ -32,6 +32,21 @@ namespace hb {
 
 static inline uint32_t round_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 
+// the record's two aux floats (layout.h: hb_aux_offset): Sum y and Sum y^2 over the warp's partial sums
+__device__ __forceinline__ void write_aux(uint8_t* rp, const RecLayout& L, float sy, float sy2, int lane) {
+    const uint32_t ao = hb_aux_offset(L);
+    if (ao == 0xFFFFFFFFu) return;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sy += __shfl_xor_sync(HB_FULL, sy, o);
+        sy2 += __shfl_xor_sync(HB_FULL, sy2, o);
+    }
+    if (lane == 0) {
+        *reinterpret_cast<float*>(rp + ao) = sy;
+        *reinterpret_cast<float*>(rp + ao + 4) = sy2;
+    }
+}
+
 // ---------------------------------------------------------------------------
 // K1: quantise rows into lane-sliced records
 // ---------------------------------------------------------------------------
@@ -50,11 +65,16 @@ __global__ void __launch_bounds__(256) quantise_kernel(const float* __restrict__
         if (!ok && lane == 0 && nan_flag) atomicOr(nan_flag, 1u);
         if (rec) {
             uint8_t* rp = rec + r * L.stride;
+            float sy = 0.0f, sy2 = 0.0f;  // aux floats (hb_aux_offset): filter inputs, any summation order will do
             for (uint32_t i = lane; i < L.dim; i += 32) {
                 float b = __fadd_rn(__fdiv_rn(__fsub_rn(v[i], mn), dl), 0.5f);
                 float f = fminf(fmaxf(floorf(b), 0.0f), 255.0f);
                 rp[hb_code_offset(L, i)] = (uint8_t)(uint32_t)f;
+                const float y = __fadd_rn(__fmul_rn(f, dl), mn);
+                sy += y;
+                sy2 += y * y;
             }
+            write_aux(rp, L, sy, sy2, lane);
             if (lane == 0) {
                 *reinterpret_cast<float*>(rp + hb_min_offset(L)) = mn;
                 *reinterpret_cast<float*>(rp + hb_delta_offset(L)) = dl;
@@ -76,10 +96,19 @@ __global__ void __launch_bounds__(256) pack_kernel(const uint8_t* __restrict__ c
     const uint64_t nwarps = (uint64_t)gridDim.x * (blockDim.x >> 5);
     for (uint64_t r = warp; r < n; r += nwarps) {
         uint8_t* rp = rec + r * L.stride;
-        for (uint32_t i = lane; i < L.dim; i += 32) rp[hb_code_offset(L, i)] = codes[r * L.dim + i];
+        const float mn = mins[r], dl = deltas[r];
+        float sy = 0.0f, sy2 = 0.0f;
+        for (uint32_t i = lane; i < L.dim; i += 32) {
+            const uint8_t c = codes[r * L.dim + i];
+            rp[hb_code_offset(L, i)] = c;
+            const float y = __fadd_rn(__fmul_rn((float)c, dl), mn);
+            sy += y;
+            sy2 += y * y;
+        }
+        write_aux(rp, L, sy, sy2, lane);
         if (lane == 0) {
-            *reinterpret_cast<float*>(rp + hb_min_offset(L)) = mins[r];
-            *reinterpret_cast<float*>(rp + hb_delta_offset(L)) = deltas[r];
+            *reinterpret_cast<float*>(rp + hb_min_offset(L)) = mn;
+            *reinterpret_cast<float*>(rp + hb_delta_offset(L)) = dl;
         }
     }
 }

@@ -93,6 +93,16 @@ HB_HD uint32_t hb_code_offset(const RecLayout& L, uint32_t i) {
     uint32_t p = 2 * L.nch + r;
     return 16 * (4 * (p / 16) + 0) + (p % 16);
 }
+// Two spare floats of a quantised record, Sum y_i and Sum y_i^2 of its dequantised values, for the search kernel's
+// pre-filter (csrc/search_fast.cuh).  Compact form: bytes 8..15 of the last word of lane 3's slice (free when
+// 16*W - 2*nch >= 8); tail form: bytes 8..15 of the tail word (free when rem == 0).  0xFFFFFFFF: no room in this layout
+// (e.g. dim 50), the search then evaluates every candidate exactly.  Written by quantise_kernel / pack_kernel; nothing
+// on the exact-arithmetic path reads them.
+HB_HD uint32_t hb_aux_offset(const RecLayout& L) {
+    if (L.kind != HB_REC_QUANT) return 0xFFFFFFFFu;
+    if (L.tail) return L.rem == 0 ? 64 * L.W + 8 : 0xFFFFFFFFu;
+    return (16 * L.W >= 2 * L.nch + 8) ? 16 * (4 * (L.W - 1) + 3) + 8 : 0xFFFFFFFFu;
+}
 HB_HD uint32_t hb_min_offset(const RecLayout& L) {
     return L.tail ? 64 * L.W : 16 * (4 * (L.W - 1) + 1) + 12;
 }

@@ -43,7 +43,10 @@ __global__ void __launch_bounds__(SEARCH_WPB * 32, MINB) search_kernel_fast(Sear
             for (uint32_t i = lane; i < p.L.dim; i += 32) qd[i] = src[i];
         }
         __syncwarp();
-        const bool ok = warp_prepare_query(p.L, qd, qd, lane);
+        // QuantVec::new on the query (quant.rs:41-66): dequantised values in place, the codes next to them
+        float qmn, qdl;
+        uint8_t* ctmp = reinterpret_cast<uint8_t*>(scratch) + 1024;  // natural-order codes (dim <= 128 bytes); qd ends below
+        const bool ok = warp_quantise(qd, p.L.dim, lane, qd, ctmp, qmn, qdl);
         __syncwarp();
         uint32_t* oid = p.out_ids + (size_t)qi * p.topn;
         float* od = p.out_dists ? p.out_dists + (size_t)qi * p.topn : nullptr;
@@ -61,6 +64,7 @@ __global__ void __launch_bounds__(SEARCH_WPB * 32, MINB) search_kernel_fast(Sear
         }
         Q q;
         q.init(p.L, qd, gl, reinterpret_cast<u64*>(wsm + FAST_OFF_QTAB), lane);
+        if (Q::kAux) q.init_filter(p.L, qd, ctmp, qmn, qdl, wsm + FAST_OFF_QCODE, gl, lane);
         SearchCounters cnt{0u, 0u, 0u, 0u};
         RegList<KPL> L;
         __syncwarp();  // every lane has copied its part of qd before the scratch area is reused
@@ -120,7 +124,7 @@ __global__ void __launch_bounds__(SEARCH_WPB * 32, MINB) search_kernel_fast(Sear
 static uint32_t buckets_for(int minb) {
     const size_t per_block = (size_t)233472 / minb - 1024;
     size_t nb = (per_block / SEARCH_WPB - FAST_OFF_TABLE) / 8;
-    nb = nb / 64 * 64;
+    nb = nb / 4 * 4;
     if (nb > 1024) nb = 1024;
     return (uint32_t)nb;
 }

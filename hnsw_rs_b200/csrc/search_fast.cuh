@@ -240,7 +240,12 @@ __device__ __noinline__ void spill_release(uint32_t* spill, SpillPool pool, int 
 #ifndef HB_FAST_ROWPF
 #define HB_FAST_ROWPF 1  // 1: the adjacency row of every admitted key is requested (L2) at admission
 #endif
+#ifndef HB_FAST_FILTER
+#define HB_FAST_FILTER 1  // 1: integer pre-filter (dp4a) before the exact evaluation, see FastQuery::prefilter
+#endif
 constexpr uint32_t FAST_QS_BYTES = HB_FAST_QSMEM ? 16 * 32 + 0 : 0;  // up to 16 chunks x 4 lanes x 8 bytes
+// pre-filter operands: the query's codes in record layout (128 bytes), (dq, dq * Sum cq, mq, Sum x^2), 32 surviving ids
+constexpr uint32_t FAST_QC_BYTES = HB_FAST_FILTER ? 128 + 16 + 128 : 0;
 
 template <int NCH, int REM>
 struct FastQuery {
@@ -252,6 +257,8 @@ struct FastQuery {
     using Rec = typename RQ::Rec;
     static constexpr int kRem = REM;
     static constexpr uint32_t kStride = 64u * W + 16u * TAIL;  // bytes per record (csrc/layout.h)
+    // the record carries Sum y and Sum y^2 (layout.h: hb_aux_offset) -> the integer pre-filter can run
+    static constexpr bool kAux = HB_FAST_FILTER && (TAIL ? (REM == 0) : (16 * W >= 2 * NCH + 8));
     // request the lines of one record (L2)
     __device__ __forceinline__ static void prefetch(const uint8_t* rp) {
         prefetch_l2(rp);
@@ -276,6 +283,8 @@ struct FastQuery {
 #endif
     float qrem;       // query value of remainder element gl (lanes gl >= REM: 0)
     u64 nz;
+    const uint4* qcode;   // pre-filter: this lane's slice of the query's codes in record layout (words gl, gl + 4, ...)
+    const float4* qaux;   // pre-filter: (dq, dq * Sum cq, mq, Sum x^2)
 
     // qd: the dequantised query in shared memory (natural order); qtab: FAST_QS_BYTES of shared memory that stay valid
     // for the whole query (only used when the query lives in shared memory)
@@ -296,6 +305,74 @@ struct FastQuery {
 #endif
         qrem = (REM > 0 && gl < REM) ? qd[8 * NCH + gl] : 0.0f;
         nz = hb_negzero2;
+        qcode = nullptr;
+        qaux = nullptr;
+    }
+    // Pre-filter operands.  ctmp: the query's codes in natural order (dim bytes); qc: 128 + 16 bytes of shared memory that
+    // stay valid for the whole query; mn / dl: the query's own quantiser.  Call after init (all 32 lanes).
+    __device__ __forceinline__ void init_filter(const RecLayout& L, const float* qd, const uint8_t* ctmp, float mn, float dl,
+                                                unsigned char* qc, int gl, int lane) {
+        uint32_t* w = reinterpret_cast<uint32_t*>(qc);
+        w[lane] = 0u;  // 128 bytes
+        __syncwarp();
+        uint32_t sc = 0;
+        float qq = 0.0f;
+        for (uint32_t i = lane; i < L.dim; i += 32) {
+            const uint32_t c = ctmp[i];
+            qc[hb_code_offset(L, i)] = (unsigned char)c;
+            sc += c;
+            qq += qd[i] * qd[i];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            sc += __shfl_xor_sync(HB_FULL, sc, o);
+            qq += __shfl_xor_sync(HB_FULL, qq, o);
+        }
+        if (lane == 0) *reinterpret_cast<float4*>(qc + 128) = make_float4(dl, dl * (float)sc, mn, qq);
+        qcode = reinterpret_cast<const uint4*>(qc) + gl;
+        qaux = reinterpret_cast<const float4*>(qc + 128);
+    }
+
+    // Integer pre-filter (the algebra of the tensor-core brute-force filter, csrc/bf_tc.cu, on CUDA cores): with
+    // x_i = cq_i*dq + mq and y_i = cb_i*db + mb,
+    //     d^2 = Sum x^2 + Sum y^2 - 2 (dq*db*<cq, cb> + (dq * Sum cq) * mb + mq * Sum y),
+    // and <cq, cb> is 8 dp4a per lane on the record bytes the lane holds anyway.  The value differs from the reference's
+    // separately rounded chain by a few 1e-7 of Sum x^2 + Sum y^2, so it only ever REJECTS: a candidate whose estimate
+    // exceeds T = worst^2 * (1 + 1e-4) by more than 1e-5 * (Sum x^2 + Sum y^2) has an exact key above the admission bound,
+    // the reference would evaluate it and drop it (searcher.rs:74-94), and so it is counted as evaluated and skipped.
+    // Everything else (NaN / inf included) goes to the exact arithmetic.  Returns "may be admitted"; meaningful in the
+    // lanes that hold the aux floats: lane 3 of a group (compact records), every lane (tail records).
+    __device__ __forceinline__ bool prefilter(const Rec& R, int gl, int gbase, float T) const {
+        const uint4 (&w)[W] = R.w;
+        float mn, dl, sy, bc;
+        if (TAIL) {
+            mn = __uint_as_float(R.tw.x);
+            dl = __uint_as_float(R.tw.y);
+            sy = __uint_as_float(R.tw.z);
+            bc = __uint_as_float(R.tw.w);
+        } else {
+            const uint32_t last = w[W - 1].w;
+            mn = __uint_as_float(__shfl_sync(HB_FULL, last, gbase + 1));
+            dl = __uint_as_float(__shfl_sync(HB_FULL, last, gbase + 2));
+            sy = __uint_as_float(w[W - 1].z);  // lane 3's own words
+            bc = __uint_as_float(last);
+        }
+        unsigned dot = 0;
+#pragma unroll
+        for (int j = 0; j < W; ++j) {
+            const uint4 q4 = qcode[4 * j];
+            dot = __dp4a(w[j].x, q4.x, dot);
+            dot = __dp4a(w[j].y, q4.y, dot);
+            dot = __dp4a(w[j].z, q4.z, dot);
+            dot = __dp4a(w[j].w, q4.w, dot);
+        }
+        dot += __shfl_xor_sync(HB_FULL, dot, 1);
+        dot += __shfl_xor_sync(HB_FULL, dot, 2);
+        const float4 a = *qaux;
+        const float t = __fmaf_rn(__fmul_rn(a.x, dl), (float)dot, __fmaf_rn(a.y, mn, __fmul_rn(a.z, sy)));
+        const float nrm = __fadd_rn(a.w, bc);
+        const float est = __fmaf_rn(-2.0f, t, nrm);
+        return !(est > __fmaf_rn(1e-5f, nrm, T));
     }
     __device__ __forceinline__ static Rec load(const uint8_t* __restrict__ rec, int gl) { return RQ::load(rec, gl); }
 
@@ -380,7 +457,9 @@ struct FastQuery {
 
 // per warp (wsm, 16-byte aligned): 32 candidate ids | spill list | worst key | scratch | visited buckets
 constexpr uint32_t FAST_OFF_SPILL = 128, FAST_OFF_WORST = FAST_OFF_SPILL + FAST_SPILL * 4, FAST_OFF_SCRATCH = FAST_OFF_WORST + 16,
-                   FAST_OFF_QTAB = FAST_OFF_SCRATCH + FAST_SCRATCH_BYTES, FAST_OFF_TABLE = FAST_OFF_QTAB + FAST_QS_BYTES;
+                   FAST_OFF_QTAB = FAST_OFF_SCRATCH + FAST_SCRATCH_BYTES, FAST_OFF_QCODE = FAST_OFF_QTAB + FAST_QS_BYTES,
+                   FAST_OFF_QAUX = FAST_OFF_QCODE + 128, FAST_OFF_SURV = FAST_OFF_QAUX + 16,
+                   FAST_OFF_TABLE = FAST_OFF_QCODE + FAST_QC_BYTES;
 
 #ifndef HB_FAST_SPEC
 #define HB_FAST_SPEC 0  // (measured: -5 %) load the adjacency row of the probable next expansion one hop ahead and prefetch its records
@@ -540,12 +619,38 @@ __device__ __forceinline__ void search_query_fast(const Q& query, const uint8_t*
 #endif
             }
             __syncwarp();
+            // ---- which of the ncnt candidates reach the exact evaluation ----
+            const uint32_t* cbuf = newbuf;  // their ids
+            int ecnt = ncnt;
+            if (Q::kAux) {
+                const u64 wk = *worst_p;
+                if (wk != RSENT) {  // |selected| == ef: a key is admitted only below the bound
+                    const float wd = __uint_as_float((uint32_t)(wk >> 32));
+                    const float T = __fmul_rn(__fmul_rn(wd, wd), 1.0001f);
+                    uint32_t* surv = reinterpret_cast<uint32_t*>(wsm + FAST_OFF_SURV);
+                    int sc = 0;
+#pragma unroll 1
+                    for (int r0 = 0; r0 < ncnt; r0 += 8) {
+                        const int idx = r0 + grp;
+                        const uint32_t cand = newbuf[idx < ncnt ? idx : 0];
+                        const bool keep = query.prefilter(Q::load(rec + (size_t)cand * Q::kStride, gl), gl, gbase, T);
+                        const bool sv = keep && gl == 3 && idx < ncnt;
+                        const unsigned sm = __ballot_sync(HB_FULL, sv);
+                        if (sv) surv[sc + __popc(sm & lt)] = cand;
+                        sc += __popc(sm);
+                    }
+                    __syncwarp();
+                    cbuf = surv;
+                    ecnt = sc;
+                }
+            }
+            if (ecnt == 0) goto next_batch;  // every candidate of the batch is above the admission bound
 #if HB_FAST_PIPE
             {
                 // two record buffers: the loads of round r+1 are in flight while round r is evaluated
                 auto rec_of = [&](int r0) {
                     const int idx = r0 + grp;
-                    return Q::load(rec + (size_t)newbuf[idx < ncnt ? idx : 0] * Q::kStride, gl);
+                    return Q::load(rec + (size_t)cbuf[idx < ecnt ? idx : 0] * Q::kStride, gl);
                 };
                 auto eval = [&](const typename Q::Rec& R, int r0) {
                     const int idx = r0 + grp;
@@ -558,11 +663,11 @@ __device__ __forceinline__ void search_query_fast(const Q& query, const uint8_t*
                 typename Q::Rec A = rec_of(0), B;
 #pragma unroll 1
                 for (int r0 = 0;; r0 += 16) {
-                    const bool moreB = r0 + 8 < ncnt;
+                    const bool moreB = r0 + 8 < ecnt;
                     if (moreB) B = rec_of(r0 + 8);
                     eval(A, r0);
                     if (!moreB) break;
-                    const bool moreA = r0 + 16 < ncnt;
+                    const bool moreA = r0 + 16 < ecnt;
                     if (moreA) A = rec_of(r0 + 16);
                     eval(B, r0 + 8);
                     if (!moreA) break;
@@ -570,9 +675,9 @@ __device__ __forceinline__ void search_query_fast(const Q& query, const uint8_t*
             }
 #else
 #pragma unroll 1
-            for (int r0 = 0; r0 < ncnt; r0 += 8) {
+            for (int r0 = 0; r0 < ecnt; r0 += 8) {
                 const int idx = r0 + grp;
-                const uint32_t cand = newbuf[idx < ncnt ? idx : 0];
+                const uint32_t cand = cbuf[idx < ecnt ? idx : 0];
                 // index.get_point(node).dist2other(point)  (searcher.rs:66-69), the sum left to the lanes below
                 u64 acc;
                 float rsq;
@@ -603,15 +708,15 @@ __device__ __forceinline__ void search_query_fast(const Q& query, const uint8_t*
             s = __fadd_rn(s, a47.z);
             s = __fadd_rn(s, a47.w);
             const float d = __fsqrt_rn(s);
-            const u64 key = make_rkey(d, newbuf[lane]);
+            const u64 key = make_rkey(d, cbuf[lane]);
             // admission (searcher.rs:74-94): key < list[ef-1] covers |selected| < ef and strict <.  `worst` is the
             // batch's starting value: a key admitted against it may still fall off the end in the merge, exactly as a
             // later, nearer key would have evicted it one by one.
-            const bool want = lane < ncnt && key < *worst_p;
+            const bool want = lane < ecnt && key < *worst_p;
             const unsigned am = __ballot_sync(HB_FULL, want);
 #if HB_FAST_ROWPF
             // an admitted key may be expanded a few hops from now: request its adjacency row (layer 0) today
-            if (want && layer == 0) prefetch_l2(g.adj0 + (size_t)newbuf[lane] * g.S0);
+            if (want && layer == 0) prefetch_l2(g.adj0 + (size_t)cbuf[lane] * g.S0);
 #endif
             if (am) {
                 __syncwarp();  // every lane has read its accumulators: the merge scratch may overwrite them
@@ -627,6 +732,7 @@ __device__ __forceinline__ void search_query_fast(const Q& query, const uint8_t*
 #endif
             }
         }
+    next_batch:
         // ---- next batch ----
         const uint32_t S = layer ? g.SU : g.S0;
         if (row != EMPTY_ID) {  // more of the current adjacency row (rows wider than 32, continuation rows)
