@@ -13,7 +13,7 @@ __host__ __device__ inline size_t fast_warp_smem(uint32_t nb) { return (size_t)F
 template <class Q, int KPL, bool STATS, int MINB>
 __global__ void __launch_bounds__(SEARCH_WPB * 32, MINB) search_kernel_fast(SearchParams p, uint32_t nb, uint32_t vmul,
                                                                            uint32_t vrsh, uint32_t* spill_ws,
-                                                                           uint32_t spill_cap) {
+                                                                           uint32_t spill_cap, uint32_t vdmax) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int gl = lane & 3;
@@ -23,6 +23,7 @@ __global__ void __launch_bounds__(SEARCH_WPB * 32, MINB) search_kernel_fast(Sear
     vis.nb = nb;
     vis.mul = vmul;
     vis.rsh = vrsh;
+    vis.dmax = vdmax;
     vis.spill = reinterpret_cast<uint32_t*>(wsm + FAST_OFF_SPILL);
     float* scratch = reinterpret_cast<float*>(wsm + FAST_OFF_SCRATCH);
     float* qd = scratch;
@@ -139,7 +140,7 @@ static cudaError_t launch_fast_s(const SearchParams& p, int num_sms, cudaStream_
     uint32_t nb = buckets_for(MINB);
     if (const char* ev = getenv("HNSWB200_FAST_NB")) {  // test knob: a small table forces the slow path and the spill list
         const uint32_t v = (uint32_t)strtoul(ev, nullptr, 10);
-        if (v > 512 && v <= nb && v % 2 == 0) nb = v;
+        if (v > 256 && v <= nb && v % 2 == 0) nb = v;
     }
     const size_t smem = fast_warp_smem(nb) * SEARCH_WPB;
     static int occ_cache_d[64] = {};
@@ -188,12 +189,17 @@ static cudaError_t launch_fast_s(const SearchParams& p, int num_sms, cudaStream_
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = overlap_previous ? 1 : 0;
-    const uint32_t vmul = 0x9E3779B1u << (32u - bbits), vrsh = 38u - bbits;
-    return cudaLaunchKernelEx(&cfg, kern, p, nb, vmul, vrsh, pool_arg ? spill_ws : (uint32_t*)nullptr, pool_arg);
+    // entry = bits [s, B) of (h * nb) mod 2^B, then the displacement: 2^s < nb keeps two ids of one bucket apart
+    const uint32_t sbits = nb > 512 ? 9u : 8u;
+    const uint32_t rembits = bbits > sbits ? bbits - sbits : 0u;
+    const uint32_t dbits = rembits <= 12 ? 3u : 15u - rembits;  // >= 2: search_fast_supported admits B <= 21 only
+    const uint32_t vmul = 0x9E3779B1u << (32u - bbits), vrsh = 32u - bbits + sbits - dbits, vdmax = (1u << dbits) - 1u;
+    return cudaLaunchKernelEx(&cfg, kern, p, nb, vmul, vrsh, pool_arg ? spill_ws : (uint32_t*)nullptr, pool_arg, vdmax);
 }
 
 #ifndef HB_FAST_MINB2
-#define HB_FAST_MINB2 8  // resident blocks per SM of the ef <= 64 variant (64 registers, 576 visited buckets)
+#define HB_FAST_MINB2 9  // resident blocks per SM of the ef <= 64 variant: 56 registers, 460 visited buckets (8 blocks x 564 buckets: -3.9 %,
+                         // profiles/r02_ab_variants.txt; the smaller table sends 5 % of the C2 queries through the exact spill set)
 #endif
 #ifndef HB_FAST_MINB4
 #define HB_FAST_MINB4 5  // ef <= 128: the visited set of such a query holds 1,000-3,000 ids, so table size counts for more than a sixth block

@@ -14,8 +14,9 @@
 //    (displacement <= 7 stored in the entry), and an id that finds 8 full buckets goes to a small exact spill list --
 //    so membership, and with it the evaluation counter, stays exact (the round-1 table over-counted after an overflow).
 //    (bucket, entry) names the id exactly: h = id * odd mod 2^B is a bijection on B-bit ids, bucket = floor(h * NB / 2^B),
-//    and the entry keeps bits [9, B) of (h * NB) mod 2^B, which differ between two ids of one bucket because those
-//    values are NB > 512 apart.
+//    and the entry keeps bits [s, B) of (h * NB) mod 2^B with 2^s < NB, which differ between two ids of one bucket because
+//    those values are NB apart (s = 9 for 512 < NB <= 1024, 8 for 256 < NB <= 512; the displacement gets the bits that
+//    are left of the 15: three, or two when B - s = 13).
 //  * distance (vectors/src/quant.rs:14-37): the four lanes of a group no longer pass the 8-way sum from lane to lane
 //    (3 dependent shuffles + sqrt + key + admission test per ROUND of 8 candidates).  Every lane stores its accumulator
 //    pair to shared memory; after the last round lane i sums the eight accumulators of candidate i in the reference's
@@ -81,7 +82,7 @@ __device__ __forceinline__ bool vis_probe(uint32_t a, uint32_t mine, bool active
 // full buckets move on (displacement + 1).  bit0 of the result: id is new (recorded now); bit1: 8 full buckets in a
 // row, the caller consults the spill list.
 __device__ __noinline__ uint32_t vis_slow(uint32_t sbase, uint32_t nb, uint32_t home, uint32_t mine0, bool pending,
-                                          bool home_full) {
+                                          bool home_full, uint32_t dmax) {
     // a lane whose home bucket was full continues behind it; a lane that lost a claim looks at its home again
     uint32_t b = home_full ? (home + 1u == nb ? 0u : home + 1u) : home, d = home_full ? 1u : 0u;
     bool isnew = false, ovf = false;
@@ -92,7 +93,7 @@ __device__ __noinline__ uint32_t vis_slow(uint32_t sbase, uint32_t nb, uint32_t 
         if (full) {
             ++d;
             b = b + 1u == nb ? 0u : b + 1u;
-            if (d > 7u) ovf = true;
+            if (d > dmax) ovf = true;
         }
         pending = pending && !found && !won && !ovf;
     }
@@ -103,7 +104,8 @@ struct VisB4 {
     uint32_t sbase;   // shared-space byte address of the table: nb buckets of 8 bytes
     uint32_t nb;      // buckets, 512 < nb <= 1024
     uint32_t mul;     // odd << (32 - B): h32 = id * mul holds the B-bit bijection value top-aligned
-    uint32_t rsh;     // 38 - B: (h32 * nb) >> rsh, low three bits cleared = entry with displacement 0
+    uint32_t rsh;     // (h32 * nb) >> rsh, low displacement bits cleared = entry with displacement 0 (see fast_vis_geometry)
+    uint32_t dmax;    // largest displacement an entry can hold (7 or 3)
     uint32_t* spill;  // ids that found 8 full buckets: [0, 14) ids, [14] their number, [15] number of ids in the global continuation
 
     __device__ __forceinline__ void clear(int lane) const {
@@ -118,13 +120,13 @@ struct VisB4 {
     __device__ __forceinline__ bool insert_warp(uint32_t id, bool want, bool& ovf) const {
         const uint32_t h32 = id * mul;
         const uint32_t home = __umulhi(h32, nb);
-        const uint32_t mine0 = ((h32 * nb) >> rsh) & 0x7FF8u;
+        const uint32_t mine0 = ((h32 * nb) >> rsh) & (0x7FFFu & ~dmax);
         bool won, full;
         const bool found = vis_probe(sbase + home * 8u, mine0, want, won, full);
         const bool pending = want && !found && !won;
         ovf = false;
         if (__any_sync(HB_FULL, pending)) {
-            const uint32_t r = vis_slow(sbase, nb, home, mine0, pending, full);
+            const uint32_t r = vis_slow(sbase, nb, home, mine0, pending, full, dmax);
             won = won || (r & 1u);
             ovf = (r & 2u) != 0u;
         }
@@ -369,10 +371,12 @@ struct FastQuery {
         dot += __shfl_xor_sync(HB_FULL, dot, 1);
         dot += __shfl_xor_sync(HB_FULL, dot, 2);
         const float4 a = *qaux;
-        const float t = __fmaf_rn(__fmul_rn(a.x, dl), (float)dot, __fmaf_rn(a.y, mn, __fmul_rn(a.z, sy)));
+        // (separate multiplies and adds: tools/check_sass.py admits no scalar FFMA in this kernel, and three instructions
+        // per round are a fair price for keeping that guard simple)
+        const float t = __fadd_rn(__fadd_rn(__fmul_rn(__fmul_rn(a.x, dl), (float)dot), __fmul_rn(a.y, mn)), __fmul_rn(a.z, sy));
         const float nrm = __fadd_rn(a.w, bc);
-        const float est = __fmaf_rn(-2.0f, t, nrm);
-        return !(est > __fmaf_rn(1e-5f, nrm, T));
+        const float est = __fadd_rn(nrm, __fmul_rn(-2.0f, t));
+        return !(est > __fadd_rn(T, __fmul_rn(1e-5f, nrm)));
     }
     __device__ __forceinline__ static Rec load(const uint8_t* __restrict__ rec, int gl) { return RQ::load(rec, gl); }
 
@@ -510,8 +514,16 @@ __device__ __forceinline__ void merge_ranked(RegList<KPL>& L, u64 key, bool want
     for (int st = C / 2; st >= 1; st >>= 1) rl += (obuf[rl + st - 1] < key) ? st : 0;
     // rank among the new keys
     int rn = 0;
+    {
+        int j = 0;
 #pragma unroll 1
-    for (int j = 0; j < m; ++j) rn += (kbuf[j] < key) ? 1 : 0;
+        for (; j + 1 < m; j += 2) {  // two keys per 16-byte (broadcast) load
+            const ulonglong2 kk = *reinterpret_cast<const ulonglong2*>(kbuf + j);
+            rn += (kk.x < key) ? 1 : 0;
+            rn += (kk.y < key) ? 1 : 0;
+        }
+        if (j < m) rn += (kbuf[j] < key) ? 1 : 0;
+    }
     const int pos = rl + rn;
     if (want) sbuf[rn] = key;  // the new keys in ascending order
     // occupancy of the merged list by new keys, one word per 32 positions

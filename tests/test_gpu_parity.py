@@ -714,7 +714,7 @@ def test_search_small_visited_table_under_heavy_load(H, oracle, monkeypatch):
     ix = to_gpu(H, orc)
     oids, odists, ocounts, ohops, oevals = orc.search_batch(queries, 10, 64, threads=8)
     spilled = 0
-    for nb in (None, "514"):
+    for nb in (None, "514", "300"):  # 300 <= 512: the entry keeps 13 bits of the hash and 2 of displacement
         if nb:
             monkeypatch.setenv("HNSWB200_FAST_NB", nb)
         ids, dists, counts, st = ix.ann_batch(queries, 10, 64, with_stats=True)
