@@ -380,6 +380,58 @@ struct FastQuery {
     }
     __device__ __forceinline__ static Rec load(const uint8_t* __restrict__ rec, int gl) { return RQ::load(rec, gl); }
 
+    // The pre-filter with TWO lanes per record (16 candidates per round instead of 8): lane h = lane & 1 of a pair holds
+    // slices h and 2 + h of the record (w[2j + e] = 16-byte word j of slice 2e + h), so that each load instruction reads one
+    // whole 32-byte sector per pair.  The dot product is an exact integer and the float expression is the one above, so
+    // the survivors are the same candidates.  Meaningful in lane h == 1 (it holds min, Sum y, Sum y^2; delta comes from
+    // lane h == 0) or in every lane (tail records).
+    struct Rec2 {
+        uint4 w[2 * W];
+        uint4 tw;
+    };
+    __device__ __forceinline__ static Rec2 load2(const uint8_t* __restrict__ rec, int h) {
+        const uint4* p = reinterpret_cast<const uint4*>(rec) + h;
+        Rec2 r;
+#pragma unroll
+        for (int j = 0; j < W; ++j) {
+            r.w[2 * j] = __ldg(p + 4 * j);
+            r.w[2 * j + 1] = __ldg(p + 4 * j + 2);
+        }
+        r.tw = make_uint4(0, 0, 0, 0);
+        if (TAIL) r.tw = __ldg(p - h + 4 * W);
+        return r;
+    }
+    __device__ __forceinline__ bool prefilter2(const Rec2& R, int h, int lane, float T) const {
+        float mn, dl, sy, bc;
+        if (TAIL) {
+            mn = __uint_as_float(R.tw.x);
+            dl = __uint_as_float(R.tw.y);
+            sy = __uint_as_float(R.tw.z);
+            bc = __uint_as_float(R.tw.w);
+        } else {
+            mn = __uint_as_float(R.w[2 * W - 2].w);                                         // slice 1 (h == 1, e == 0)
+            dl = __uint_as_float(__shfl_sync(HB_FULL, R.w[2 * W - 1].w, lane & ~1));         // slice 2 (h == 0, e == 1)
+            sy = __uint_as_float(R.w[2 * W - 1].z);                                         // slice 3 (h == 1, e == 1)
+            bc = __uint_as_float(R.w[2 * W - 1].w);
+        }
+        const uint4* qc2 = reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(qaux) - 128) + h;
+        unsigned dot = 0;
+#pragma unroll
+        for (int j = 0; j < 2 * W; ++j) {
+            const uint4 q4 = qc2[2 * j];  // word j/2 of slice 2*(j%2) + h: 16-byte index 4*(j/2) + 2*(j%2) + h
+            dot = __dp4a(R.w[j].x, q4.x, dot);
+            dot = __dp4a(R.w[j].y, q4.y, dot);
+            dot = __dp4a(R.w[j].z, q4.z, dot);
+            dot = __dp4a(R.w[j].w, q4.w, dot);
+        }
+        dot += __shfl_xor_sync(HB_FULL, dot, 1);
+        const float4 a = *qaux;
+        const float t = __fadd_rn(__fadd_rn(__fmul_rn(__fmul_rn(a.x, dl), (float)dot), __fmul_rn(a.y, mn)), __fmul_rn(a.z, sy));
+        const float nrm = __fadd_rn(a.w, bc);
+        const float est = __fadd_rn(nrm, __fmul_rn(-2.0f, t));
+        return !(est > __fadd_rn(T, __fmul_rn(1e-5f, nrm)));
+    }
+
     // acc: this lane's accumulator pair (acc[2gl], acc[2gl+1]) after the full chunks; rsq: the square of remainder
     // element gl (meaningful for gl < REM).  All 32 lanes call together.
     __device__ __forceinline__ void partial(const Rec& R, int gl, int gbase, u64& acc_out, float& rsq) const {
@@ -468,6 +520,12 @@ constexpr uint32_t FAST_OFF_SPILL = 128, FAST_OFF_WORST = FAST_OFF_SPILL + FAST_
 #ifndef HB_FAST_SPEC
 #define HB_FAST_SPEC 0  // (measured: -5 %) load the adjacency row of the probable next expansion one hop ahead and prefetch its records
 #endif
+#ifndef HB_FAST_FILTER2
+#define HB_FAST_FILTER2 1  // the pre-filter runs with two lanes per record (16 candidates per round)
+#endif
+#ifndef HB_FAST_INS1
+#define HB_FAST_INS1 1  // a batch that admits exactly one key inserts it in registers (no shared-memory merge)
+#endif
 #ifndef HB_FAST_MERGE
 #define HB_FAST_MERGE 1  // 1: merge_ranked below; 0: RegList::merge (round 1)
 #endif
@@ -501,6 +559,30 @@ __device__ __forceinline__ void merge_ranked(RegList<KPL>& L, u64 key, bool want
                                              int& len, int ef, int lane, u64* worst_p) {
     constexpr int C = 32 * KPL;
     const int m = __popc(am);
+#if HB_FAST_INS1
+    if (m == 1) {
+        // one new key (the usual case once the list is full): an insertion in registers.  p = number of list keys below it;
+        // slot q keeps its key (q < p), takes the new one (q == p) or the key one place to its left (q > p).
+        const u64 k1 = __shfl_sync(HB_FULL, key, __ffs(am) - 1);
+        int p = 0;
+#pragma unroll
+        for (int s = 0; s < KPL; ++s) p += __popc(__ballot_sync(HB_FULL, L.v[s] < k1));
+        const u64 from_left = __shfl_up_sync(HB_FULL, L.v[KPL - 1], 1);
+        const int newlen = min(ef, len + 1);
+#pragma unroll
+        for (int s = KPL - 1; s >= 0; --s) {  // downwards: L.v[s - 1] is still the old key when slot s reads it
+            const int q = lane * KPL + s;
+            const u64 left = s ? L.v[s ? s - 1 : 0] : from_left;
+            u64 v = q < p ? L.v[s] : (q == p ? k1 : left);
+            v = q < newlen ? v : RSENT;
+            L.v[s] = v;
+            if (q == ef - 1 && newlen == ef) *worst_p = v;
+        }
+        len = newlen;
+        __syncwarp();
+        return;
+    }
+#endif
     // old list -> shared memory (position lane*KPL + s), compacted new keys -> kbuf
 #pragma unroll
     for (int s = 0; s < KPL; s += 2)
@@ -641,6 +723,18 @@ __device__ __forceinline__ void search_query_fast(const Q& query, const uint8_t*
                     const float T = __fmul_rn(__fmul_rn(wd, wd), 1.0001f);
                     uint32_t* surv = reinterpret_cast<uint32_t*>(wsm + FAST_OFF_SURV);
                     int sc = 0;
+#if HB_FAST_FILTER2
+#pragma unroll 1
+                    for (int r0 = 0; r0 < ncnt; r0 += 16) {
+                        const int idx = r0 + (lane >> 1), h = lane & 1;
+                        const uint32_t cand = newbuf[idx < ncnt ? idx : 0];
+                        const bool keep = query.prefilter2(Q::load2(rec + (size_t)cand * Q::kStride, h), h, lane, T);
+                        const bool sv = keep && h == 1 && idx < ncnt;
+                        const unsigned sm = __ballot_sync(HB_FULL, sv);
+                        if (sv) surv[sc + __popc(sm & lt)] = cand;
+                        sc += __popc(sm);
+                    }
+#else
 #pragma unroll 1
                     for (int r0 = 0; r0 < ncnt; r0 += 8) {
                         const int idx = r0 + grp;
@@ -651,6 +745,7 @@ __device__ __forceinline__ void search_query_fast(const Q& query, const uint8_t*
                         if (sv) surv[sc + __popc(sm & lt)] = cand;
                         sc += __popc(sm);
                     }
+#endif
                     __syncwarp();
                     cbuf = surv;
                     ecnt = sc;
