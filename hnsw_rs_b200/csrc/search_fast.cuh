@@ -389,16 +389,28 @@ struct FastQuery {
         uint4 w[2 * W];
         uint4 tw;
     };
-    __device__ __forceinline__ static Rec2 load2(const uint8_t* __restrict__ rec, int h) {
+    __device__ __forceinline__ static Rec2 load2(const uint8_t* __restrict__ rec, int h, bool act) {
         const uint4* p = reinterpret_cast<const uint4*>(rec) + h;
         Rec2 r;
+        const uint4 z = make_uint4(0, 0, 0, 0);
 #pragma unroll
         for (int j = 0; j < W; ++j) {
-            r.w[2 * j] = __ldg(p + 4 * j);
-            r.w[2 * j + 1] = __ldg(p + 4 * j + 2);
+            r.w[2 * j] = act ? __ldg(p + 4 * j) : z;
+            r.w[2 * j + 1] = act ? __ldg(p + 4 * j + 2) : z;
         }
-        r.tw = make_uint4(0, 0, 0, 0);
-        if (TAIL) r.tw = __ldg(p - h + 4 * W);
+        r.tw = z;
+        if (TAIL) r.tw = act ? __ldg(p - h + 4 * W) : z;
+        return r;
+    }
+    // a group without a candidate in this round loads nothing
+    __device__ __forceinline__ static Rec load_if(const uint8_t* __restrict__ rec, int gl, bool act) {
+        const uint4* p = reinterpret_cast<const uint4*>(rec);
+        Rec r;
+        const uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int j = 0; j < W; ++j) r.w[j] = act ? __ldg(p + 4 * j + gl) : z;
+        r.tw = z;
+        if (TAIL) r.tw = act ? __ldg(p + 4 * W) : z;
         return r;
     }
     __device__ __forceinline__ bool prefilter2(const Rec2& R, int h, int lane, float T) const {
@@ -523,8 +535,11 @@ constexpr uint32_t FAST_OFF_SPILL = 128, FAST_OFF_WORST = FAST_OFF_SPILL + FAST_
 #ifndef HB_FAST_FILTER2
 #define HB_FAST_FILTER2 1  // the pre-filter runs with two lanes per record (16 candidates per round)
 #endif
+#ifndef HB_FAST_PREDLD
+#define HB_FAST_PREDLD 0  // 1: groups / pairs without a candidate in a round do not load a record (measured: -2 %, the selects cost more than the requests)
+#endif
 #ifndef HB_FAST_INS1
-#define HB_FAST_INS1 1  // a batch that admits exactly one key inserts it in registers (no shared-memory merge)
+#define HB_FAST_INS1 3  // a batch that admits at most this many keys inserts them in registers (no shared-memory merge); 0: off
 #endif
 #ifndef HB_FAST_MERGE
 #define HB_FAST_MERGE 1  // 1: merge_ranked below; 0: RegList::merge (round 1)
@@ -560,29 +575,34 @@ __device__ __forceinline__ void merge_ranked(RegList<KPL>& L, u64 key, bool want
     constexpr int C = 32 * KPL;
     const int m = __popc(am);
 #if HB_FAST_INS1
-    if (m == 1) {
-        // one new key (the usual case once the list is full): an insertion in registers.  p = number of list keys below it;
-        // slot q keeps its key (q < p), takes the new one (q == p) or the key one place to its left (q > p).
-        const u64 k1 = __shfl_sync(HB_FULL, key, __ffs(am) - 1);
-        int p = 0;
+    if (m <= HB_FAST_INS1) {
+        // one new key (or a few): insertions in registers, one after the other.  p = number of list keys below the key;
+        // slot q keeps its key (q < p), takes the new one (q == p) or the key one place to its left (q > p); a key that is
+        // no longer below the bound by the time its turn comes has p == ef and falls off the end, as in the merge.
+#pragma unroll 1
+        for (unsigned todo = am; todo; todo &= todo - 1u) {
+            const u64 k1 = __shfl_sync(HB_FULL, key, __ffs(todo) - 1);
+            int p = 0;
 #pragma unroll
-        for (int s = 0; s < KPL; ++s) p += __popc(__ballot_sync(HB_FULL, L.v[s] < k1));
-        const u64 from_left = __shfl_up_sync(HB_FULL, L.v[KPL - 1], 1);
-        const int newlen = min(ef, len + 1);
+            for (int s = 0; s < KPL; ++s) p += __popc(__ballot_sync(HB_FULL, L.v[s] < k1));
+            const u64 from_left = __shfl_up_sync(HB_FULL, L.v[KPL - 1], 1);
+            const int newlen = min(ef, len + 1);
 #pragma unroll
-        for (int s = KPL - 1; s >= 0; --s) {  // downwards: L.v[s - 1] is still the old key when slot s reads it
-            const int q = lane * KPL + s;
-            const u64 left = s ? L.v[s ? s - 1 : 0] : from_left;
-            u64 v = q < p ? L.v[s] : (q == p ? k1 : left);
-            v = q < newlen ? v : RSENT;
-            L.v[s] = v;
-            if (q == ef - 1 && newlen == ef) *worst_p = v;
+            for (int s = KPL - 1; s >= 0; --s) {  // downwards: L.v[s - 1] is still the old key when slot s reads it
+                const int q = lane * KPL + s;
+                const u64 left = s ? L.v[s ? s - 1 : 0] : from_left;
+                u64 v = q < p ? L.v[s] : (q == p ? k1 : left);
+                v = q < newlen ? v : RSENT;
+                L.v[s] = v;
+                if (q == ef - 1 && newlen == ef) *worst_p = v;
+            }
+            len = newlen;
         }
-        len = newlen;
         __syncwarp();
         return;
     }
 #endif
+    __syncwarp();  // every lane has read its accumulators: the merge scratch may overwrite them
     // old list -> shared memory (position lane*KPL + s), compacted new keys -> kbuf
 #pragma unroll
     for (int s = 0; s < KPL; s += 2)
@@ -728,7 +748,7 @@ __device__ __forceinline__ void search_query_fast(const Q& query, const uint8_t*
                     for (int r0 = 0; r0 < ncnt; r0 += 16) {
                         const int idx = r0 + (lane >> 1), h = lane & 1;
                         const uint32_t cand = newbuf[idx < ncnt ? idx : 0];
-                        const bool keep = query.prefilter2(Q::load2(rec + (size_t)cand * Q::kStride, h), h, lane, T);
+                        const bool keep = query.prefilter2(Q::load2(rec + (size_t)cand * Q::kStride, h, HB_FAST_PREDLD ? idx < ncnt : true), h, lane, T);
                         const bool sv = keep && h == 1 && idx < ncnt;
                         const unsigned sm = __ballot_sync(HB_FULL, sv);
                         if (sv) surv[sc + __popc(sm & lt)] = cand;
@@ -788,7 +808,7 @@ __device__ __forceinline__ void search_query_fast(const Q& query, const uint8_t*
                 // index.get_point(node).dist2other(point)  (searcher.rs:66-69), the sum left to the lanes below
                 u64 acc;
                 float rsq;
-                query.partial(Q::load(rec + (size_t)cand * Q::kStride, gl), gl, gbase, acc, rsq);
+                query.partial(Q::load_if(rec + (size_t)cand * Q::kStride, gl, HB_FAST_PREDLD ? idx < ecnt : true), gl, gbase, acc, rsq);
                 *reinterpret_cast<u64*>(accbuf + idx * FAST_ACC_STRIDE + 2 * gl) = acc;
                 if (Q::kRem > 0) accbuf[idx * FAST_ACC_STRIDE + 8 + gl] = rsq;
             }
@@ -814,7 +834,9 @@ __device__ __forceinline__ void search_query_fast(const Q& query, const uint8_t*
             s = __fadd_rn(s, a47.y);
             s = __fadd_rn(s, a47.z);
             s = __fadd_rn(s, a47.w);
-            const float d = __fsqrt_rn(s);
+            // lanes without a candidate hold stale scratch bytes: give them a value on the square root's fast path, or the
+            // whole warp waits for their slow path (denormal / NaN inputs) in four batches out of five
+            const float d = __fsqrt_rn(lane < ecnt ? s : 1.0f);
             const u64 key = make_rkey(d, cbuf[lane]);
             // admission (searcher.rs:74-94): key < list[ef-1] covers |selected| < ef and strict <.  `worst` is the
             // batch's starting value: a key admitted against it may still fall off the end in the merge, exactly as a
@@ -826,10 +848,10 @@ __device__ __forceinline__ void search_query_fast(const Q& query, const uint8_t*
             if (want && layer == 0) prefetch_l2(g.adj0 + (size_t)cbuf[lane] * g.S0);
 #endif
             if (am) {
-                __syncwarp();  // every lane has read its accumulators: the merge scratch may overwrite them
 #if HB_FAST_MERGE
                 merge_ranked<KPL>(L, key, want, am, obuf, kbuf, sbuf, len, ef_l, lane, worst_p);
 #else
+                __syncwarp();  // every lane has read its accumulators: the merge scratch may overwrite them
                 const int kcnt = __popc(am);
                 if (want) kbuf[__popc(am & lt)] = key;
                 __syncwarp();
