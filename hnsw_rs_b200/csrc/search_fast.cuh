@@ -715,7 +715,7 @@ __device__ __forceinline__ void search_query_fast(const Q& query, const uint8_t*
         isnew = isnew && !seed;
         const unsigned nm = __ballot_sync(HB_FULL, isnew);
         const int ncnt = __popc(nm);
-#if HB_FAST_SPEC
+#if HB_FAST_SPEC == 1
         if (spec_pending) {
             // the row of the probable next expansion has arrived by now (it was requested at the pop): request the records
             // of its neighbours a whole hop before they are evaluated
@@ -901,6 +901,7 @@ __device__ __forceinline__ void search_query_fast(const Q& query, const uint8_t*
                 if (cid == spec_id) {  // the guess of the previous hop was right: its row is already here
                     nb = spec_nb;
                     have_nb = true;
+                    fresh_row = HB_FAST_SPEC != 1;  // (mode 1 requested the records of this row a hop ago)
                 }
                 // guess the next expansion: the best entry that is still unexpanded.  The reference pops exactly that one
                 // next unless this batch admits a nearer key (searcher.rs:36-44); a wrong guess costs one row load.
@@ -909,7 +910,7 @@ __device__ __forceinline__ void search_query_fast(const Q& query, const uint8_t*
                 if (list_peek<KPL>(L, c2)) {
                     spec_id = c2;
                     spec_nb = ((uint32_t)lane < g.S0) ? __ldg(g.adj0 + (size_t)c2 * g.S0 + lane) : EMPTY_ID;
-                    spec_pending = true;
+                    spec_pending = HB_FAST_SPEC == 1;
                 }
             }
 #endif
