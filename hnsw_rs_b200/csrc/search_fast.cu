@@ -203,12 +203,9 @@ static cudaError_t launch_fast_s(const SearchParams& p, int num_sms, cudaStream_
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = overlap_previous ? 1 : 0;
-    // entry = bits [s, B) of (h * nb) mod 2^B, then the displacement: 2^s < nb keeps two ids of one bucket apart
-    const uint32_t sbits = nb > 512 ? 9u : 8u;
-    const uint32_t rembits = bbits > sbits ? bbits - sbits : 0u;
-    const uint32_t dbits = rembits <= 12 ? 3u : 15u - rembits;  // >= 2: search_fast_supported admits B <= 21 only
-    const uint32_t vmul = 0x9E3779B1u << (32u - bbits), vrsh = 32u - bbits + sbits - dbits, vdmax = (1u << dbits) - 1u;
-    return cudaLaunchKernelEx(&cfg, kern, p, nb, vmul, vrsh, pool_arg ? spill_ws : (uint32_t*)nullptr, pool_arg, vdmax);
+    // entry = bits [s, B) of (h * nb) mod 2^B, then the displacement (csrc/vis_geometry.h; search_fast_supported admits B <= 21 only)
+    const FastVisGeometry vg = fast_vis_geometry(bbits, nb);
+    return cudaLaunchKernelEx(&cfg, kern, p, nb, vg.mul, vg.rsh, pool_arg ? spill_ws : (uint32_t*)nullptr, pool_arg, vg.dmax);
 }
 
 #ifndef HB_FAST_MINB2

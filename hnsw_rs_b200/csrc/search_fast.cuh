@@ -29,6 +29,7 @@
 #pragma once
 #include "search_params.cuh"
 #include "search_reg.cuh"
+#include "vis_geometry.h"
 
 #ifndef HB_FAST_PREFETCH_ALL
 #define HB_FAST_PREFETCH_ALL 1  // request the record of every neighbour before the visited test (see search_reg.cuh)
@@ -190,9 +191,8 @@ struct VisB4 {
     // results.insert_visited for all 32 lanes (want: this lane holds an id).  Returns "id was not yet visited" per
     // lane; ovf: the table could not decide for this lane (see vis_slow), isnew is then false and the caller decides.
     __device__ __forceinline__ bool insert_warp(uint32_t id, bool want, bool& ovf) const {
-        const uint32_t h32 = id * mul;
-        const uint32_t home = __umulhi(h32, nb);
-        const uint32_t mine0 = ((h32 * nb) >> rsh) & (0x7FFFu & ~dmax);
+        uint32_t home, mine0;
+        fast_vis_slot(mul, rsh, dmax, nb, id, home, mine0);
         bool won, full;
         const bool found = vis_probe(sbase + home * 8u, mine0, want, won, full);
         const bool pending = want && !found && !won;
@@ -208,9 +208,8 @@ struct VisB4 {
     // overflowed (HB_FAST_MATCH / HB_FAST_SPILLNEST).
     template <class OVF>
     __device__ __forceinline__ bool insert_warp(uint32_t id, bool want, int lane, OVF&& on_ovf) const {
-        const uint32_t h32 = id * mul;
-        const uint32_t home = __umulhi(h32, nb);
-        const uint32_t mine0 = ((h32 * nb) >> rsh) & (0x7FFFu & ~dmax);
+        uint32_t home, mine0;
+        fast_vis_slot(mul, rsh, dmax, nb, id, home, mine0);
         bool won, full;
 #if HB_FAST_MATCH
         // One step without a read-back: the lanes that want the same home bucket (match.any) take its free entries in

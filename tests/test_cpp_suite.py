@@ -51,3 +51,12 @@ def test_record_layouts():
     _build()
     r = subprocess.run([os.path.join(ROOT, "tests", "cpp", "layout_test")], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "all checks passed" in r.stdout, r.stdout[-2000:]
+
+
+def test_visited_set_geometry_names_every_id():
+    """vis_geometry.h (shared by the launcher, the kernel's VisB4 and this test): for every id below 2^B the pair
+    (home bucket, 15-bit entry) is unique -- exhaustively, B = 10..21, every bucket count the launcher can produce -- so the
+    bucketed visited set of search_kernel_fast has no false positives (results.rs:101-103 stays exact); host only."""
+    _build()
+    r = subprocess.run([os.path.join(ROOT, "tests", "cpp", "visgeom_test")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "visgeom ok" in r.stdout, r.stdout[-2000:]
