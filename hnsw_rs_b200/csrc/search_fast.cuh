@@ -35,34 +35,15 @@
 #define HB_FAST_PREFETCH_ALL 1  // request the record of every neighbour before the visited test (see search_reg.cuh)
 #endif
 
-#ifndef HB_FAST_MATCH
-#define HB_FAST_MATCH 0  // 1: the new ids of a batch that share a home bucket take its free entries in lane order (one match.any):
-                         // no claim read-back in the first step and no lost claims, see VisB4::insert_warp.  Measured: -2.4 %
-                         // (call U): MATCH.ANY costs more than the read-back and the lost claims (10 % of the batches) it removes
-#endif
-#ifndef HB_FAST_SPILLNEST
-#define HB_FAST_SPILLNEST 1  // 1: the exact spill set is consulted inside the slow-path branch (an id can only overflow there) instead
-                             // of behind a vote of its own in every batch (+0.65 %, profiles/r02_ab_variants.txt call U)
-#endif
+// (measured and removed, profiles/r02_ab_variants.txt calls U-W: handing out the free entries of a home bucket by lane rank with one
+// match.any instead of claim + read-back: -2.4 %; L1 / L2 eviction hints on the record and row loads: +-0.2 %, except
+// L1::no_allocate on the pre-filter's record loads: -24 %, the four 16-byte loads of a record no longer merge into one request per line)
 #ifndef HB_FAST_SLOWINL
 #define HB_FAST_SLOWINL 1  // 1: vis_slow is inlined at its one call site (no call, no packing of the predicates into registers:
                            // 29 % of the batches go there; +0.95 %, call U)
 #endif
 #ifndef HB_FAST_PRMTPOP
 #define HB_FAST_PRMTPOP 1  // 1: the free marks of a bucket are counted on the four high bytes gathered by one byte permute (call V)
-#endif
-// L1 eviction hints of the search's global loads (0: plain read-only load; 1: L1::evict_last; 2: L1::no_allocate; 3: L1::evict_first)
-#ifndef HB_FAST_LDF
-#define HB_FAST_LDF 0  // record loads of the pre-filter (the survivors are loaded again by the exact rounds)
-#endif
-#ifndef HB_FAST_LDX
-#define HB_FAST_LDX 0  // record loads of the exact rounds (last use of the record in this batch)
-#endif
-#ifndef HB_FAST_LDR
-#define HB_FAST_LDR 0  // adjacency row loads (a row is read once per query)
-#endif
-#ifndef HB_FAST_ROWPF_EL
-#define HB_FAST_ROWPF_EL 0  // 1: the adjacency row requested at admission is marked L2::evict_last
 #endif
 #if HB_FAST_SLOWINL
 #define HB_VIS_SLOW_ATTR __forceinline__
@@ -91,31 +72,6 @@ __device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v) {
     asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "r"(v) : "memory");
 }
 
-// 16 bytes of a record through the read-only path, with an L1 eviction hint (see HB_FAST_LDF)
-template <int HINT>
-__device__ __forceinline__ uint4 ld_rec(const uint4* p) {
-    uint4 v;
-    if (HINT == 1)
-        asm volatile("ld.global.nc.L1::evict_last.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-    else if (HINT == 2)
-        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-    else if (HINT == 3)
-        asm volatile("ld.global.nc.L1::evict_first.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-    else
-        v = __ldg(p);
-    return v;
-}
-template <int HINT>
-__device__ __forceinline__ uint32_t ld_u32(const uint32_t* p) {
-    uint32_t v;
-    if (HINT == 2)
-        asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
-    else if (HINT == 3)
-        asm volatile("ld.global.nc.L1::evict_first.u32 %0, [%1];" : "=r"(v) : "l"(p));
-    else
-        v = __ldg(p);
-    return v;
-}
 // number of free entries (0xFFFF; valid entries are < 0x8000) of a bucket
 __device__ __forceinline__ int vis_free(uint32_t w0, uint32_t w1) {
 #if HB_FAST_PRMTPOP
@@ -153,9 +109,6 @@ __device__ __forceinline__ bool vis_probe(uint32_t a, uint32_t mine, bool active
 // row, the caller consults the spill list.
 __device__ HB_VIS_SLOW_ATTR uint32_t vis_slow(uint32_t sbase, uint32_t nb, uint32_t home, uint32_t mine0, bool pending,
                                               bool home_full, uint32_t dmax) {
-#if HB_FAST_MATCH
-    __syncwarp();  // the first step's claims (no read-back there) are in place before the next bucket is read
-#endif
     // a lane whose home bucket was full continues behind it; a lane that lost a claim looks at its home again
     uint32_t b = home_full ? (home + 1u == nb ? 0u : home + 1u) : home, d = home_full ? 1u : 0u;
     bool isnew = false, ovf = false;
@@ -188,68 +141,24 @@ struct VisB4 {
         if (lane == 0) { spill[FAST_SPILL_N1] = 0u; spill[FAST_SPILL_N2] = 0u; }
         __syncwarp();
     }
-    // results.insert_visited for all 32 lanes (want: this lane holds an id).  Returns "id was not yet visited" per
-    // lane; ovf: the table could not decide for this lane (see vis_slow), isnew is then false and the caller decides.
-    __device__ __forceinline__ bool insert_warp(uint32_t id, bool want, bool& ovf) const {
+    // results.insert_visited for all 32 lanes (want: this lane holds an id).  Returns "id was not yet visited" per lane.
+    // Where the table cannot decide for a lane (ovf: 8 full buckets in a row, see vis_slow) the caller's exact spill set
+    // does: on_ovf(isnew, ovf) -> isnew, called by all lanes when any lane overflowed.  That call sits inside the slow-path
+    // branch -- an id can only overflow there -- and not behind a vote of its own in every batch (+0.65 %,
+    // profiles/r02_ab_variants.txt call U).
+    template <class OVF>
+    __device__ __forceinline__ bool insert_warp(uint32_t id, bool want, OVF&& on_ovf) const {
         uint32_t home, mine0;
         fast_vis_slot(mul, rsh, dmax, nb, id, home, mine0);
         bool won, full;
         const bool found = vis_probe(sbase + home * 8u, mine0, want, won, full);
         const bool pending = want && !found && !won;
-        ovf = false;
         if (__any_sync(HB_FULL, pending)) {
             const uint32_t r = vis_slow(sbase, nb, home, mine0, pending, full, dmax);
             won = won || (r & 1u);
-            ovf = (r & 2u) != 0u;
+            const bool ovf = (r & 2u) != 0u;
+            if (__any_sync(HB_FULL, ovf)) won = on_ovf(won, ovf);  // rare
         }
-        return won;
-    }
-    // The same with the overflow handling passed in: on_ovf(isnew, ovf) -> isnew, called by all lanes when any lane
-    // overflowed (HB_FAST_MATCH / HB_FAST_SPILLNEST).
-    template <class OVF>
-    __device__ __forceinline__ bool insert_warp(uint32_t id, bool want, int lane, OVF&& on_ovf) const {
-        uint32_t home, mine0;
-        fast_vis_slot(mul, rsh, dmax, nb, id, home, mine0);
-        bool won, full;
-#if HB_FAST_MATCH
-        // One step without a read-back: the lanes that want the same home bucket (match.any) take its free entries in
-        // lane order, rank r gets entry (4 - e) + r.  A lane whose rank is beyond the free entries finds the bucket full
-        // by the time the lower ranks have written, which is exactly the state a later lookup of its id sees: it
-        // continues behind the home bucket like any id that met a full one.
-        const uint32_t a = sbase + home * 8u;
-        uint32_t w0, w1;
-        lds_v2(a, w0, w1);
-        const uint32_t pat = mine0 * 0x10001u;
-        const uint32_t x0 = w0 ^ pat, x1 = w1 ^ pat;
-        const uint32_t z = (((x0 - 0x00010001u) & ~x0) | ((x1 - 0x00010001u) & ~x1)) & 0x80008000u;
-        const int e = vis_free(w0, w1);
-        const bool need = want && z == 0u;
-        const unsigned peers = __match_any_sync(HB_FULL, need ? home : (0x80000000u | (uint32_t)lane));
-        const int r = __popc(peers & ((1u << lane) - 1u));
-        won = need && r < e;
-        if (won) sts_u16(a + 8u - 2u * (uint32_t)(e - r), mine0);
-        full = need && !won;
-        const bool pending = full;
-#else
-        const bool found = vis_probe(sbase + home * 8u, mine0, want, won, full);
-        const bool pending = want && !found && !won;
-#endif
-#if HB_FAST_SPILLNEST
-        if (__any_sync(HB_FULL, pending)) {
-            const uint32_t r2 = vis_slow(sbase, nb, home, mine0, pending, full, dmax);
-            won = won || (r2 & 1u);
-            const bool ovf = (r2 & 2u) != 0u;
-            if (__any_sync(HB_FULL, ovf)) won = on_ovf(won, ovf);  // rare: 8 full buckets in a row
-        }
-#else
-        bool ovf = false;
-        if (__any_sync(HB_FULL, pending)) {
-            const uint32_t r2 = vis_slow(sbase, nb, home, mine0, pending, full, dmax);
-            won = won || (r2 & 1u);
-            ovf = (r2 & 2u) != 0u;
-        }
-        if (__any_sync(HB_FULL, ovf)) won = on_ovf(won, ovf);  // rare: 8 full buckets in a row
-#endif
         return won;
     }
 };
@@ -515,11 +424,11 @@ struct FastQuery {
         const uint4 z = make_uint4(0, 0, 0, 0);
 #pragma unroll
         for (int j = 0; j < W; ++j) {
-            r.w[2 * j] = act ? ld_rec<HB_FAST_LDF>(p + 4 * j) : z;
-            r.w[2 * j + 1] = act ? ld_rec<HB_FAST_LDF>(p + 4 * j + 2) : z;
+            r.w[2 * j] = act ? __ldg(p + 4 * j) : z;
+            r.w[2 * j + 1] = act ? __ldg(p + 4 * j + 2) : z;
         }
         r.tw = z;
-        if (TAIL) r.tw = act ? ld_rec<HB_FAST_LDF>(p - h + 4 * W) : z;
+        if (TAIL) r.tw = act ? __ldg(p - h + 4 * W) : z;
         return r;
     }
     // a group without a candidate in this round loads nothing
@@ -528,9 +437,9 @@ struct FastQuery {
         Rec r;
         const uint4 z = make_uint4(0, 0, 0, 0);
 #pragma unroll
-        for (int j = 0; j < W; ++j) r.w[j] = act ? ld_rec<HB_FAST_LDX>(p + 4 * j + gl) : z;
+        for (int j = 0; j < W; ++j) r.w[j] = act ? __ldg(p + 4 * j + gl) : z;
         r.tw = z;
-        if (TAIL) r.tw = act ? ld_rec<HB_FAST_LDX>(p + 4 * W) : z;
+        if (TAIL) r.tw = act ? __ldg(p + 4 * W) : z;
         return r;
     }
     __device__ __forceinline__ bool prefilter2(const Rec2& R, int h, int lane, float T) const {
@@ -825,21 +734,11 @@ __device__ __forceinline__ void search_query_fast(const Q& query, const uint8_t*
         if (fresh_row && valid) Q::prefetch(rec + (size_t)nb * Q::kStride);
 #endif
         fresh_row = false;
-#if HB_FAST_MATCH || HB_FAST_SPILLNEST
-        bool isnew = vis.insert_warp(nb, valid, lane, [&](bool isnew_in, bool ovf) -> bool {
+        bool isnew = vis.insert_warp(nb, valid, [&](bool isnew_in, bool ovf) -> bool {
             const uint32_t r = vis_spill<KPL>(vis.spill, pool, __ballot_sync(HB_FULL, ovf), nb, isnew_in, L, lane);
             if (STATS) cnt.overflow |= r & 6u;
             return (r & 1u) != 0u;
         });
-#else
-        bool ovf;
-        bool isnew = vis.insert_warp(nb, valid, ovf);
-        if (__any_sync(HB_FULL, ovf)) {  // rare: 8 full buckets in a row
-            const uint32_t r = vis_spill<KPL>(vis.spill, pool, __ballot_sync(HB_FULL, ovf), nb, isnew, L, lane);
-            isnew = (r & 1u) != 0u;
-            if (STATS) cnt.overflow |= r & 6u;
-        }
-#endif
         isnew = isnew && !seed;
         const unsigned nm = __ballot_sync(HB_FULL, isnew);
         const int ncnt = __popc(nm);
@@ -973,11 +872,7 @@ __device__ __forceinline__ void search_query_fast(const Q& query, const uint8_t*
             const unsigned am = __ballot_sync(HB_FULL, want);
 #if HB_FAST_ROWPF
             // an admitted key may be expanded a few hops from now: request its adjacency row (layer 0) today
-#if HB_FAST_ROWPF_EL
-            if (want && layer == 0) asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(g.adj0 + (size_t)cbuf[lane] * g.S0));
-#else
             if (want && layer == 0) prefetch_l2(g.adj0 + (size_t)cbuf[lane] * g.S0);
-#endif
 #endif
             if (am) {
 #if HB_FAST_MERGE
@@ -993,9 +888,6 @@ __device__ __forceinline__ void search_query_fast(const Q& query, const uint8_t*
 #endif
             }
         }
-#if HB_FAST_MATCH
-        else __syncwarp();  // (the other path has one behind newbuf) this batch's claims are in place before the next batch reads the table
-#endif
     next_batch:
         // ---- next batch ----
         const uint32_t S = layer ? g.SU : g.S0;
@@ -1054,7 +946,7 @@ __device__ __forceinline__ void search_query_fast(const Q& query, const uint8_t*
             const uint32_t* adj = layer ? g.upper_adj : g.adj0;
             const uint32_t* rp = adj + (size_t)row * S;
             const uint32_t i = b0 + lane;
-            nb = (i < S) ? ld_u32<HB_FAST_LDR>(rp + i) : EMPTY_ID;
+            nb = (i < S) ? __ldg(rp + i) : EMPTY_ID;
             fresh_row = true;
         }
         {
