@@ -10,7 +10,7 @@
 //    read once; "is it there" is one zero-halfword test over the two words, "where does it go" is a population count
 //    of the empty marks (entries fill a bucket front to back and are never removed).  One claim + read-back step
 //    instead of a lock-step probe loop (4.2 steps x 23 instructions per batch in round 1).  A full home bucket or a
-//    lost claim (two new ids of one batch, same bucket) goes to an out-of-line loop over the following buckets
+//    lost claim (two new ids of one batch, same bucket) goes to a continuation loop (vis_slow) over the following buckets
 //    (displacement <= 7 stored in the entry), and an id that finds 8 full buckets goes to a small exact spill list --
 //    so membership, and with it the evaluation counter, stays exact (the round-1 table over-counted after an overflow).
 //    (bucket, entry) names the id exactly: h = id * odd mod 2^B is a bijection on B-bit ids, bucket = floor(h * NB / 2^B),
@@ -104,7 +104,7 @@ __device__ __forceinline__ bool vis_probe(uint32_t a, uint32_t mine, bool active
     return found;
 }
 
-// Out-of-line continuation for the lanes the single-step insert could not settle: lost claims retry the same bucket,
+// Continuation for the lanes the single-step insert could not settle (29 % of the batches on C2; inlined at its one call site): lost claims retry the same bucket,
 // full buckets move on (displacement + 1).  bit0 of the result: id is new (recorded now); bit1: 8 full buckets in a
 // row, the caller consults the spill list.
 __device__ HB_VIS_SLOW_ATTR uint32_t vis_slow(uint32_t sbase, uint32_t nb, uint32_t home, uint32_t mine0, bool pending,
