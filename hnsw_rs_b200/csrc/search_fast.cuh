@@ -104,8 +104,8 @@ __device__ __forceinline__ bool vis_probe(uint32_t a, uint32_t mine, bool active
     return found;
 }
 
-// Continuation for the lanes the single-step insert could not settle (29 % of the batches on C2; inlined at its one call site): lost claims retry the same bucket,
-// full buckets move on (displacement + 1).  bit0 of the result: id is new (recorded now); bit1: 8 full buckets in a
+// Continuation for the lanes the single-step insert could not settle (29 % of the batches on C2; inlined at its one
+// call site): lost claims retry the same bucket, full buckets move on (displacement + 1).  bit0 of the result: id is new (recorded now); bit1: 8 full buckets in a
 // row, the caller consults the spill list.
 __device__ HB_VIS_SLOW_ATTR uint32_t vis_slow(uint32_t sbase, uint32_t nb, uint32_t home, uint32_t mine0, bool pending,
                                               bool home_full, uint32_t dmax) {
